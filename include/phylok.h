@@ -1,0 +1,162 @@
+/* phylok.h -- C ABI of the B200-native phyloK2 tree-kernel path (libphylok.so).
+ *
+ * The reference (ArtPoon/kamphir) has no FFI for this path: the boundary is the Python class
+ * `PhyloKernel` (phyloK2.py:9-236) that `Kamphir` inherits (kamphir.py:34,54).  Every entry point below
+ * names the reference interface it replaces (paths relative to /root/reference).  The Python mirror of the
+ * class (kamphir_b200/phylokernel.py) binds these with ctypes; INTEGRATION.md shows the stub a kamphir
+ * maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns a pk_status (0 = ok, < 0 = error) and
+ * leaves a thread-local message retrievable with pk_last_error().  Input buffers are borrowed for the call,
+ * output buffers are caller-owned, opaque handles are library-owned until the matching *_free/_destroy.
+ * There is no CPU fallback: device entry points fail with PK_ERR_NODEVICE/PK_ERR_CUDA when no sm_100 GPU is usable.
+ */
+#ifndef PHYLOK_H
+#define PHYLOK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PK_ABI_VERSION 1
+
+typedef enum pk_status {
+    PK_OK = 0,
+    PK_ERR_INVALID = -1,   /* bad argument or tree the kernel is not defined for (non-binary, NaN length, empty) -> ValueError */
+    PK_ERR_PARSE = -2,     /* Newick syntax error                                                                 -> ValueError */
+    PK_ERR_CUDA = -3,      /* CUDA runtime error                                                                  -> RuntimeError */
+    PK_ERR_NOMEM = -4,
+    PK_ERR_NODEVICE = -5   /* no usable GPU: the product path never falls back to the CPU                         -> RuntimeError */
+} pk_status;
+
+/* normalize_tree modes, phyloK2.py:101-130 ('none' = skipped, kamphir.py:616) */
+enum { PK_NORM_NONE = 0, PK_NORM_MEAN = 1, PK_NORM_MEDIAN = 2 };
+
+/* tree preparation flags: the caller-side prep sequence of kamphir.py:153-156 / :279-282 */
+enum {
+    PK_PREP_ZERO_ROOT = 1,  /* tree.root.branch_length = 0          kamphir.py:153,279 */
+    PK_PREP_LADDERIZE = 2,  /* tree.ladderize()  (ascending #tips, stable)  kamphir.py:154,280; phyloK2.py:77-78 */
+    PK_PREP_KAMPHIR = 3
+};
+
+typedef struct pk_tree pk_tree;       /* host: one flattened, annotated tree (annotate_tree, phyloK2.py:132-146) */
+typedef struct pk_ctx pk_ctx;         /* one GPU + stream + scratch pool; create lazily, never before fork() (kamphir.py:638) */
+typedef struct pk_forest pk_forest;   /* device-resident packed SoA of a set of trees */
+
+/* kernel parameters = PhyloKernel.__init__ keywords, phyloK2.py:10-22 */
+typedef struct pk_params {
+    double decay;       /* decayFactor, lambda   (kamphir -kdecay, kamphir.py:608) */
+    double gauss;       /* gaussFactor, tau      (kamphir -tau,    kamphir.py:611) */
+    double sigma;       /* sigma, additive constant in prod(sigma + C(child)), phyloK2.py:194-199 */
+    int32_t precision;  /* 64: fp64 end to end (1e-9 rel.)   32: fp32 cells, fp64 accumulation (1e-5 rel.) */
+    int32_t reserved;
+} pk_params;
+
+typedef struct pk_tree_info {
+    int32_t n_internal;   /* len(get_nonterminals()) */
+    int32_t n_tips;       /* len(get_terminals()) */
+    int32_t n_levels;     /* wavefront depth: 1 + max height of an internal node above the cherries */
+    int32_t n_classes;    /* production classes: 3 unlabelled, 1 + 2S + S*S with S tip states */
+    int32_t n_states;     /* 0 = unlabelled */
+    int32_t reserved;
+    double height;        /* max root-to-tip depth before normalisation (kamphir.py:118-119,255-256) */
+    double scale;         /* divisor applied by normalize_tree (1 when PK_NORM_NONE) */
+} pk_tree_info;
+
+/* ---- library ------------------------------------------------------------------------------------- */
+int pk_abi_version(void);
+const char *pk_last_error(void);
+int pk_device_count(void);                       /* CUDA devices visible, 0 when none / no driver */
+
+/* ---- host side: Newick -> flattened tree (replaces Bio.Phylo parse + kamphir prep + annotate_tree) ----
+ * pk_tree_from_newick : Phylo.read (kamphir.py:323) + prep (kamphir.py:279-282) + annotate (phyloK2.py:132-146)
+ * pk_trees_from_newick: Phylo.parse over a multi-tree handle (kamphir.py:112, phyloK2.py:74); returns an array
+ *                       allocated by the library (free each tree, then pk_tree_array_free).
+ * n_states > 0 turns on tip-state productions: state = integer after the last '_' of the tip name
+ *                       (rcolgem.py:274,376,588); extension with no reference implementation.
+ * nthreads: worker threads for the multi-tree form (<= 0: hardware concurrency). */
+int pk_tree_from_newick(const char *text, size_t len, int prep_flags, int normalize, int n_states, pk_tree **out);
+int pk_trees_from_newick(const char *text, size_t len, int prep_flags, int normalize, int n_states, int nthreads,
+                         pk_tree ***out, int32_t *n_out);
+void pk_tree_array_free(pk_tree **arr);
+
+/* pk_tree_from_arrays: a tree already walked by the caller (the Python mirror walks Bio.Phylo-like objects in
+ * get_nonterminals(order='postorder') order, phyloK2.py:166-167).  cidx[2*i+s] = post-order index of the internal
+ * child in slot s or -1 for a tip; bl[2*i+s] = that child's branch length (node.bl, phyloK2.py:144-145);
+ * cls = NULL (production = #tip children + 1, phyloK2.py:141-142) or explicit class ids in [0, n_classes). */
+int pk_tree_from_arrays(int32_t n_internal, const int32_t *cidx, const double *bl, const uint8_t *cls,
+                        int32_t n_classes, pk_tree **out);
+void pk_tree_free(pk_tree *t);
+int pk_tree_get_info(const pk_tree *t, pk_tree_info *info);
+/* post-order arrays as annotate_tree defines them (for parity tests): prod[n], cprod[2n], cidx[2n], bl[2n] */
+int pk_tree_export(const pk_tree *t, uint8_t *prod, uint8_t *cprod, int32_t *cidx, double *bl);
+/* ascending heights of the internal nodes above the deepest tip, un-normalised (kamphir.py:255-258,147-149) */
+int pk_tree_node_heights(const pk_tree *t, double *heights /* n_internal */);
+/* exact work of one DP: counts = {node pairs, matched cells M, child-cell reads R} */
+int pk_pair_counts(const pk_tree *a, const pk_tree *b, int64_t counts[3]);
+/* kcoal of kamphir.py:260-269: cosine of the two ascending node-height vectors (sim indexed into target) */
+int pk_kcoal(const pk_tree *sim, const pk_tree *target, double *out);
+
+/* ---- device side ------------------------------------------------------------------------------------ */
+int pk_ctx_create(int device, pk_ctx **out);
+void pk_ctx_destroy(pk_ctx *ctx);
+int pk_ctx_set_stream(pk_ctx *ctx, void *cuda_stream);   /* run on a caller-owned cudaStream_t (NULL = own stream) */
+int pk_ctx_sync(pk_ctx *ctx);
+/* tuning knobs (0 = default): threads per CTA, CTAs per SM for the HBM-resident path */
+int pk_ctx_configure(pk_ctx *ctx, int32_t threads, int32_t ctas_per_sm, int32_t force_hbm);
+/* the most recent DP kernel launch on this ctx: ms = its device time (CUDA events recorded around that launch on the
+ * ctx stream; blocks until it finished), launches = DP kernels launched since ctx creation, path = 0 (C in shared
+ * memory) / 1 (C in HBM slabs), launch_cfg = {grid, threads per CTA, dynamic shared memory bytes}. Any may be NULL. */
+int pk_ctx_last_stats(pk_ctx *ctx, double *ms, int64_t *launches, int32_t *path, int32_t launch_cfg[3]);
+
+int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_t n, int32_t precision, pk_forest **out);
+void pk_forest_free(pk_forest *f);
+int pk_forest_bytes(const pk_forest *f, int64_t *bytes);
+/* exact work of a pair list / of one Gram part: counts = {DPs, node pairs, matched cells M, child reads R} */
+int pk_forest_pair_stats(const pk_forest *fa, const pk_forest *fb, const int32_t *pairs, int64_t npairs, int64_t counts[4]);
+int pk_forest_gram_stats(const pk_forest *f, int32_t tile, int32_t part, int32_t nparts, int64_t counts[4]);
+
+/* PhyloKernel.kernel (phyloK2.py:158-209) for a list of pairs: out[p] = K(A[pairs[2p]], B[pairs[2p+1]]).
+ * Host-resident form: uploads, launches, copies back (this is what PhyloKernel.kernel/kernel_batch call). */
+int pk_kernel_pairs(pk_ctx *ctx, const pk_tree *const *A, int32_t nA, const pk_tree *const *B, int32_t nB,
+                    const int32_t *pairs, int32_t npairs, const pk_params *params, double *out_k);
+/* Device-resident form: forests already in HBM; pairs and out are DEVICE pointers; asynchronous on the ctx stream. */
+int pk_forest_kernel_pairs(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, const int32_t *d_pairs,
+                           int32_t npairs, const pk_params *params, double *d_out_k);
+
+/* The ABC objective's inner loop, kamphir.py:288-306 + :434-450, for one target tree and nsims replicates:
+ *   k[s] = K(obs, sim_s), denom[s] = K(sim_s, sim_s), khat[s] = exp(log k - (log ref_denom + log denom)/2).
+ * *ref_denom = K(obs,obs) (kamphir.py:157) is computed when passed as NaN or <= 0 and returned. Any output may be NULL. */
+int pk_score_batch(pk_ctx *ctx, const pk_tree *obs, const pk_tree *const *sims, int32_t nsims, const pk_params *params,
+                   double *ref_denom, double *out_k, double *out_denom, double *out_khat);
+
+/* All-pairs Gram matrix, the working form of PhyloKernel.compute_matrix (phyloK2.py:148-156): out is N x N row-major,
+ * symmetric; normalised = 0: raw K (reference semantics); 1: K / sqrt(K_ii K_jj).  Host-resident form. */
+int pk_gram(pk_ctx *ctx, const pk_tree *const *trees, int32_t n, const pk_params *params, int normalised, double *out);
+/* Device-resident, shardable form.  The upper triangle is cut into tile x tile blocks, block t belongs to part
+ * t % nparts; this call computes the blocks of `part` and writes both (i,j) and (j,i) into d_out (N x N, leading
+ * dimension ld, DEVICE pointer -- may be a peer/IPC mapping of another GPU's buffer so results cross NVLink once,
+ * written by the DP kernel itself).  d_diag (N doubles, device) receives K_ii; it is computed by every part.
+ * Asynchronous on the ctx stream. */
+int pk_forest_gram_part(pk_ctx *ctx, const pk_forest *f, const pk_params *params, int normalised, int32_t tile,
+                        int32_t part, int32_t nparts, double *d_out, int64_t ld, double *d_diag);
+/* DPs that pk_forest_gram_part(part, nparts) evaluates (excluding the N diagonal DPs every part repeats) */
+int pk_gram_part_pairs(int32_t n, int32_t tile, int32_t part, int32_t nparts, int64_t *npairs);
+
+/* cross-process sharing of a device buffer (one result matrix on rank 0, written by all ranks over NVLink) */
+int pk_device_alloc(pk_ctx *ctx, size_t bytes, void **d_ptr);
+int pk_device_free(pk_ctx *ctx, void *d_ptr);
+int pk_ipc_export(pk_ctx *ctx, void *d_ptr, unsigned char handle[64]);
+int pk_ipc_open(pk_ctx *ctx, const unsigned char handle[64], void **d_ptr);
+int pk_ipc_close(pk_ctx *ctx, void *d_ptr);
+int pk_memcpy_d2h(pk_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+int pk_memcpy_h2d(pk_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+int pk_memset_d(pk_ctx *ctx, void *d_dst, int value, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHYLOK_H */

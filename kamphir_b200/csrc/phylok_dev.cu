@@ -1,0 +1,960 @@
+// Device side of libphylok.so: the node-pair DP of PhyloKernel.kernel (phyloK2.py:158-209) as a height-level
+// wavefront on sm_100a, plus the batched drivers (pair list, sim-vs-obs batch, Gram tiles).
+//
+//   C(i,j) = lambda * exp(-((a0-b0)^2 + (a1-b1)^2) / tau) * prod_{s=0,1} f_s          (phyloK2.py:184-199)
+//   f_s    = 1                       if the slot-s children have different productions
+//          = sigma + lambda          if both are tips
+//          = sigma + C(ci_s, cj_s)   otherwise
+//   K      = sum of C over production-matched internal-node pairs                      (phyloK2.py:203-204)
+//
+// One CTA evaluates one tree pair (persistent CTAs pull pairs from an atomic work counter).  Both trees' packed
+// node blocks are staged into shared memory with one TMA bulk copy each (cp.async.bulk + mbarrier).  Nodes are
+// stored in "kernel order" (class, level, post-order), so the matched cells of a pair form one dense
+// cntA[c] x cntB[c] rectangle per production class c and C is stored compactly as those rectangles (M cells, not
+// n1*n2).  The tree with fewer levels supplies the rows; level L of the wavefront is then a contiguous row range
+// of each rectangle, evaluated by all warps (a lane owns a column and keeps that node's data in registers while it
+// walks the rows), followed by one __syncthreads.  Child cells live in strictly lower rows, so they are final.
+// Small pairs keep C in shared memory; large pairs keep it in a per-CTA slab in HBM (L2-resident when the slabs of
+// all resident CTAs fit the 126 MB L2): coalesced row writes, predicated child-cell gathers.
+// No tensor cores (not a contraction), no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "phylok_internal.h"
+
+#define PK_CUDA(call)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t e__ = (call);                                                                           \
+        if (e__ != cudaSuccess)                                                                             \
+            return pk_fail(PK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));               \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// work description
+// ---------------------------------------------------------------------------------------------------
+struct DpArgs {
+    const unsigned char *blocksA;   // packed tree blocks of forest A
+    const int4 *metaA;              // per tree: {offset / 16, bytes, n, nlev}
+    const unsigned char *blocksB;
+    const int4 *metaB;
+    int mode;                       // 0: explicit pair list, 1: Gram tiles, 2: diagonal (i,i)
+    const int2 *pairs;              // mode 0
+    const int2 *tiles;              // mode 1: tile coordinates (ti, tj), tj >= ti
+    int tile_shift;                 // log2(tile edge)
+    int n_trees;                    // mode 1/2
+    long long total;                // work items
+    double *out;                    // mode 0: out[w]; mode 1: out[i*ld+j] and out[j*ld+i]; mode 2: out[i]
+    long long ld;
+    const double *diag;             // mode 1, optional: write K / sqrt(diag[i]*diag[j])
+    double lambda, neg_inv_tau, sigma;
+    void *scratch;                  // HBM path: per-CTA C slabs
+    long long slab_elems;
+    unsigned long long *counter;    // work counter
+    int tree_region;                // bytes reserved per staged tree block in shared memory
+    int rowinfo_bytes;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA bulk copy (global -> shared)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(void *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, void *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+__device__ __forceinline__ double pk_exp(double x) { return exp(x); }
+__device__ __forceinline__ float pk_exp(float x) { return __expf(x); }
+
+// ---------------------------------------------------------------------------------------------------
+// the DP kernel
+// ---------------------------------------------------------------------------------------------------
+template <typename T, bool CSMEM, int NT>
+__global__ void __launch_bounds__(NT) pk_dp_kernel(const DpArgs a) {
+    constexpr int NW = NT / 32;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ long long s_work[2];
+    __shared__ int s_coff[PK_MAX_CLASSES + 1];
+    __shared__ int s_cntB[PK_MAX_CLASSES];
+    __shared__ double s_part[32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char *sA = smem;
+    unsigned char *sB = smem + a.tree_region;
+    int4 *rowinfo = reinterpret_cast<int4 *>(smem + 2 * (size_t)a.tree_region);
+    T *C = CSMEM ? reinterpret_cast<T *>(smem + 2 * (size_t)a.tree_region + a.rowinfo_bytes)
+                 : reinterpret_cast<T *>(a.scratch) + (size_t)blockIdx.x * (size_t)a.slab_elems;
+
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    uint32_t parity = 0;
+    const T lambda = (T)a.lambda, sigma = (T)a.sigma, neg_inv_tau = (T)a.neg_inv_tau;
+
+    for (unsigned it_no = 0;; ++it_no) {
+        if (tid == 0) s_work[it_no & 1] = (long long)atomicAdd(a.counter, 1ull);
+        __syncthreads();
+        const long long w = s_work[it_no & 1];
+        if (w >= a.total) break;
+
+        // ---- which pair ------------------------------------------------------------------------
+        int ia, ib;
+        if (a.mode == 0) {
+            const int2 p = a.pairs[w];
+            ia = p.x;
+            ib = p.y;
+        } else if (a.mode == 1) {
+            const int sh = a.tile_shift;
+            const long long tile = w >> (2 * sh);
+            const int r = (int)(w & ((1ll << (2 * sh)) - 1));
+            const int2 t = a.tiles[tile];
+            ia = (t.x << sh) + (r >> sh);
+            ib = (t.y << sh) + (r & ((1 << sh) - 1));
+            if (ib < ia || ib >= a.n_trees || ia >= a.n_trees) continue;
+        } else {
+            ia = ib = (int)w;
+        }
+        const int4 mA = a.metaA[ia], mB = a.metaB[ib];
+        const bool swap = mA.w > mB.w;   // rows come from the tree with fewer wavefront levels (K is symmetric)
+        const unsigned char *srcR = swap ? a.blocksB + (size_t)mB.x * 16 : a.blocksA + (size_t)mA.x * 16;
+        const unsigned char *srcC = swap ? a.blocksA + (size_t)mA.x * 16 : a.blocksB + (size_t)mB.x * 16;
+        const uint32_t bytesR = swap ? mB.y : mA.y, bytesC = swap ? mA.y : mB.y;
+
+        // ---- stage both node blocks with TMA bulk copies ---------------------------------------
+        if (tid == 0) {
+            mbar_expect_tx(&s_bar, bytesR + bytesC);
+            tma_bulk_g2s(sA, srcR, bytesR, &s_bar);
+            tma_bulk_g2s(sB, srcC, bytesC, &s_bar);
+        }
+        mbar_wait(&s_bar, parity);
+        parity ^= 1;
+
+        const int *hA = reinterpret_cast<const int *>(sA);
+        const int *hB = reinterpret_cast<const int *>(sB);
+        const int nA = hA[0], ncls = hA[1], nlevA = hA[2];
+        const int *clsA = reinterpret_cast<const int *>(sA + hA[4]);
+        const int *lvlA = reinterpret_cast<const int *>(sA + hA[5]);
+        const T *a0p = reinterpret_cast<const T *>(sA + hA[6]);
+        const T *a1p = reinterpret_cast<const T *>(sA + hA[7]);
+        const int *codeA0 = reinterpret_cast<const int *>(sA + hA[8]);
+        const int *codeA1 = reinterpret_cast<const int *>(sA + hA[9]);
+        const int *clsB = reinterpret_cast<const int *>(sB + hB[4]);
+        const T *b0p = reinterpret_cast<const T *>(sB + hB[6]);
+        const T *b1p = reinterpret_cast<const T *>(sB + hB[7]);
+        const int *codeB0 = reinterpret_cast<const int *>(sB + hB[8]);
+        const int *codeB1 = reinterpret_cast<const int *>(sB + hB[9]);
+
+        // ---- compact C layout: cell 0 holds lambda (the "tip x tip" value), then one rectangle per class
+        if (tid == 0) {
+            int off = 1;
+            for (int c = 0; c < ncls; ++c) {
+                const int wB = clsB[c + 1] - clsB[c];
+                s_cntB[c] = wB;
+                s_coff[c] = off;
+                off += (clsA[c + 1] - clsA[c]) * wB;
+            }
+            s_coff[ncls] = off;
+            C[0] = lambda;
+        }
+        __syncthreads();
+        // per row: {class+1 of child 0, C offset of child 0's row, same for child 1}
+        for (int r = tid; r < nA; r += NT) {
+            const int c0 = codeA0[r], c1 = codeA1[r];
+            const int q0 = c0 >> 24, q1 = c1 >> 24;
+            int4 ri;
+            ri.x = q0;
+            ri.y = q0 ? s_coff[q0 - 1] + (c0 & 0xffffff) * s_cntB[q0 - 1] : 0;
+            ri.z = q1;
+            ri.w = q1 ? s_coff[q1 - 1] + (c1 & 0xffffff) * s_cntB[q1 - 1] : 0;
+            rowinfo[r] = ri;
+        }
+        __syncthreads();
+
+        // ---- wavefront over the row tree's levels ------------------------------------------------
+        double acc = 0.0;
+        for (int L = 0; L < nlevA; ++L) {
+            int itembase = 0;
+            for (int c = 0; c < ncls; ++c) {
+                const int r0 = lvlA[c * (nlevA + 1) + L], r1 = lvlA[c * (nlevA + 1) + L + 1];
+                const int rows = r1 - r0, wB = s_cntB[c];
+                if (rows <= 0 || wB <= 0) continue;
+                const int nch = (wB + 31) >> 5;
+                // balanced split of the (column chunk, row) space of this rectangle over the warps: each warp gets a
+                // contiguous run of rows of one column chunk (spilling into the next chunk at most once or twice)
+                const int total = rows * nch;
+                const int per = (total + NW - 1) / NW;
+                const int colbase = clsB[c], rowcls = clsA[c], coff = s_coff[c];
+                int wv = warp - (itembase % NW);
+                if (wv < 0) wv += NW;
+                int idx = wv * per;
+                const int end = min(total, idx + per);
+                if (idx < end) {
+                    int ch = idx / rows;
+                    int r = idx - ch * rows;
+                    while (idx < end) {
+                        const int rcount = min(rows - r, end - idx);
+                        const int jb = (ch << 5) + lane;
+                        if (jb < wB) {
+                            const int col = colbase + jb;
+                            const T b0 = b0p[col], b1 = b1p[col];
+                            const int cb0 = codeB0[col], cb1 = codeB1[col];
+                            const int qb0 = cb0 >> 24, kb0 = cb0 & 0xffffff, qb1 = cb1 >> 24, kb1 = cb1 & 0xffffff;
+                            const int rbeg = r0 + r, rend = rbeg + rcount;
+                            T *crow = C + coff + (size_t)(rbeg - rowcls) * wB + jb;
+                            T part = (T)0;
+                            for (int rr = rbeg; rr < rend; ++rr, crow += wB) {
+                                const T d0 = a0p[rr] - b0, d1 = a1p[rr] - b1;
+                                const int4 ri = rowinfo[rr];
+                                T v = lambda * pk_exp((d0 * d0 + d1 * d1) * neg_inv_tau);
+                                if (ri.x == qb0) v *= sigma + C[ri.y + kb0];
+                                if (ri.z == qb1) v *= sigma + C[ri.w + kb1];
+                                *crow = v;
+                                part += v;
+                            }
+                            acc += (double)part;
+                        }
+                        idx += rcount;
+                        r = 0;
+                        ++ch;
+                    }
+                }
+                itembase += (total + per - 1) / per;
+            }
+            __syncthreads();
+        }
+
+        // ---- deterministic block reduction of K ---------------------------------------------------
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_part[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double k = 0.0;
+            for (int i = 0; i < NW; ++i) k += s_part[i];
+            if (a.mode == 0) {
+                a.out[w] = k;
+            } else if (a.mode == 1) {
+                if (a.diag) k = k / sqrt(a.diag[ia] * a.diag[ib]);
+                a.out[(long long)ia * a.ld + ib] = k;
+                a.out[(long long)ib * a.ld + ia] = k;
+            } else {
+                a.out[ia] = k;
+            }
+        }
+        // the next iteration's first __syncthreads orders these reads before the staging buffers are overwritten
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// context / forest
+// ---------------------------------------------------------------------------------------------------
+struct pk_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int cfg_threads = 0, cfg_ctas = 0, cfg_force_hbm = 0;
+    void *d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    unsigned long long *d_counters = nullptr;   // ring of work counters (one per launch in flight)
+    int counter_next = 0;
+    void *d_tmp = nullptr;                      // staging for pair lists / tiles / results of the host-resident forms
+    size_t tmp_bytes = 0;
+    void *h_pinned = nullptr;
+    size_t pinned_bytes = 0;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool ev_valid = false;
+    long long launches = 0;
+    int last_path = 0;
+    int last_grid = 0, last_threads = 0, last_smem = 0;
+};
+
+struct pk_forest {
+    pk_ctx *ctx = nullptr;
+    int32_t n = 0;
+    int32_t precision = 64;
+    int32_t ncls = 3;
+    unsigned char *d_blocks = nullptr;
+    int4 *d_meta = nullptr;
+    size_t bytes = 0;
+    int32_t max_block = 0, max_n = 0;
+    std::vector<int32_t> max_cnt;   // per class, max node count over the trees
+    std::vector<int32_t> cnt;       // [n][ncls]
+    std::vector<int64_t> hist;      // [n][ncls*2*(ncls+1)]
+    std::vector<int32_t> nint;      // [n]
+};
+
+static const int kCounterRing = 64;
+
+static int ensure_device(pk_ctx *ctx) {
+    PK_CUDA(cudaSetDevice(ctx->device));
+    return PK_OK;
+}
+
+extern "C" int pk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int pk_ctx_create(int device, pk_ctx **out) {
+    if (!out) return pk_fail(PK_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return pk_fail(PK_ERR_NODEVICE, std::string("no CUDA device available (") +
+                                            (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                                            "); this library has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return pk_fail(PK_ERR_INVALID, "device index out of range");
+    cudaDeviceProp prop;
+    PK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return pk_fail(PK_ERR_NODEVICE, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                            std::to_string(prop.minor) + "; this library is built for sm_100a only");
+    pk_ctx *ctx = new pk_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    cudaError_t err = cudaSetDevice(device);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * kCounterRing);
+    if (err == cudaSuccess) err = cudaEventCreate(&ctx->ev[0]);
+    if (err == cudaSuccess) err = cudaEventCreate(&ctx->ev[1]);
+    if (err != cudaSuccess) {
+        delete ctx;
+        return pk_fail(PK_ERR_CUDA, std::string("pk_ctx_create: ") + cudaGetErrorString(err));
+    }
+    *out = ctx;
+    return PK_OK;
+}
+
+extern "C" void pk_ctx_destroy(pk_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_tmp) cudaFree(ctx->d_tmp);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
+    if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int pk_ctx_set_stream(pk_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return pk_fail(PK_ERR_INVALID, "null ctx");
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+        ctx->own_stream = false;
+    } else {
+        PK_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return PK_OK;
+}
+
+extern "C" int pk_ctx_sync(pk_ctx *ctx) {
+    if (!ctx) return pk_fail(PK_ERR_INVALID, "null ctx");
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PK_OK;
+}
+
+extern "C" int pk_ctx_configure(pk_ctx *ctx, int32_t threads, int32_t ctas_per_sm, int32_t force_hbm) {
+    if (!ctx) return pk_fail(PK_ERR_INVALID, "null ctx");
+    if (threads != 0 && threads != 128 && threads != 256 && threads != 512 && threads != 1024)
+        return pk_fail(PK_ERR_INVALID, "threads must be 0, 128, 256, 512 or 1024");
+    ctx->cfg_threads = threads;
+    ctx->cfg_ctas = ctas_per_sm;
+    ctx->cfg_force_hbm = force_hbm;
+    return PK_OK;
+}
+
+extern "C" int pk_ctx_last_stats(pk_ctx *ctx, double *ms, int64_t *launches, int32_t *path, int32_t launch_cfg[3]) {
+    if (!ctx) return pk_fail(PK_ERR_INVALID, "null ctx");
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    if (ms) {
+        *ms = 0.0;
+        if (ctx->ev_valid) {
+            PK_CUDA(cudaEventSynchronize(ctx->ev[1]));
+            float f = 0.f;
+            PK_CUDA(cudaEventElapsedTime(&f, ctx->ev[0], ctx->ev[1]));
+            *ms = f;
+        }
+    }
+    if (launches) *launches = ctx->launches;
+    if (path) *path = ctx->last_path;
+    if (launch_cfg) {
+        launch_cfg[0] = ctx->last_grid;
+        launch_cfg[1] = ctx->last_threads;
+        launch_cfg[2] = ctx->last_smem;
+    }
+    return PK_OK;
+}
+
+static int ensure_tmp(pk_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->tmp_bytes) return PK_OK;
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_tmp) cudaFree(ctx->d_tmp);
+    ctx->d_tmp = nullptr;
+    ctx->tmp_bytes = 0;
+    size_t want = std::max(bytes, (size_t)1 << 20);
+    PK_CUDA(cudaMalloc(&ctx->d_tmp, want));
+    ctx->tmp_bytes = want;
+    return PK_OK;
+}
+
+static int ensure_pinned(pk_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_bytes) return PK_OK;
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    ctx->h_pinned = nullptr;
+    ctx->pinned_bytes = 0;
+    size_t want = std::max(bytes, (size_t)1 << 20);
+    PK_CUDA(cudaMallocHost(&ctx->h_pinned, want));
+    ctx->pinned_bytes = want;
+    return PK_OK;
+}
+
+static int ensure_scratch(pk_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return PK_OK;
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    ctx->d_scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    PK_CUDA(cudaMalloc(&ctx->d_scratch, bytes));
+    ctx->scratch_bytes = bytes;
+    return PK_OK;
+}
+
+extern "C" int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_t n, int32_t precision, pk_forest **out) {
+    if (!ctx || !trees || !out) return pk_fail(PK_ERR_INVALID, "null argument");
+    if (n < 1) return pk_fail(PK_ERR_INVALID, "empty tree set");
+    if (precision != 64 && precision != 32) return pk_fail(PK_ERR_INVALID, "precision must be 64 or 32");
+    *out = nullptr;
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    const int ncls = trees[0] ? trees[0]->ncls : 0;
+    size_t total = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        if (!trees[i]) return pk_fail(PK_ERR_INVALID, "null tree in set");
+        if (trees[i]->ncls != ncls) return pk_fail(PK_ERR_INVALID, "trees use different production class schemes");
+        total += pk_block_bytes(*trees[i], precision);
+    }
+    if (total / 16 > 0x7fffffffull) return pk_fail(PK_ERR_INVALID, "tree set too large for one forest");
+    pk_forest *f = new pk_forest();
+    f->ctx = ctx;
+    f->n = n;
+    f->precision = precision;
+    f->ncls = ncls;
+    f->bytes = total;
+    f->max_cnt.assign(ncls, 0);
+    f->cnt.resize((size_t)n * ncls);
+    f->hist.resize((size_t)n * ncls * 2 * (ncls + 1));
+    f->nint.resize(n);
+    const size_t meta_bytes = sizeof(int4) * (size_t)n;
+    rc = ensure_pinned(ctx, total + meta_bytes);
+    if (rc) {
+        delete f;
+        return rc;
+    }
+    unsigned char *h = static_cast<unsigned char *>(ctx->h_pinned);
+    int4 *hmeta = reinterpret_cast<int4 *>(h + total);
+    size_t off = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        const pk_tree &t = *trees[i];
+        const size_t b = pk_block_bytes(t, precision);
+        pk_block_pack(t, precision, h + off);
+        hmeta[i] = make_int4((int)(off / 16), (int)b, t.n, t.nlev);
+        f->max_block = std::max<int32_t>(f->max_block, (int32_t)b);
+        f->max_n = std::max(f->max_n, t.n);
+        f->nint[i] = t.n;
+        for (int c = 0; c < ncls; ++c) {
+            int cnt = t.cls_start[c + 1] - t.cls_start[c];
+            f->cnt[(size_t)i * ncls + c] = cnt;
+            f->max_cnt[c] = std::max(f->max_cnt[c], cnt);
+        }
+        std::copy(t.hist.begin(), t.hist.end(), f->hist.begin() + (size_t)i * t.hist.size());
+        off += b;
+    }
+    cudaError_t e = cudaMalloc(&f->d_blocks, total + meta_bytes);
+    if (e == cudaSuccess) {
+        f->d_meta = reinterpret_cast<int4 *>(f->d_blocks + total);
+        e = cudaMemcpyAsync(f->d_blocks, h, total + meta_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // the pinned staging buffer is reused
+    if (e != cudaSuccess) {
+        if (f->d_blocks) cudaFree(f->d_blocks);
+        delete f;
+        return pk_fail(PK_ERR_CUDA, std::string("pk_forest_upload: ") + cudaGetErrorString(e));
+    }
+    *out = f;
+    return PK_OK;
+}
+
+extern "C" void pk_forest_free(pk_forest *f) {
+    if (!f) return;
+    cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->stream);
+    if (f->d_blocks) cudaFree(f->d_blocks);
+    delete f;
+}
+
+extern "C" int pk_forest_bytes(const pk_forest *f, int64_t *bytes) {
+    if (!f || !bytes) return pk_fail(PK_ERR_INVALID, "null argument");
+    *bytes = (int64_t)(f->bytes + sizeof(int4) * (size_t)f->n);
+    return PK_OK;
+}
+
+// exact work counts {DPs, node pairs, matched cells M, child reads R}
+static void pair_work(const pk_forest *fa, int i, const pk_forest *fb, int j, int64_t c[4]) {
+    const int ncls = fa->ncls;
+    const size_t hs = (size_t)ncls * 2 * (ncls + 1);
+    int64_t m = 0, r = 0;
+    for (int k = 0; k < ncls; ++k) {
+        m += (int64_t)fa->cnt[(size_t)i * ncls + k] * fb->cnt[(size_t)j * ncls + k];
+        for (int s = 0; s < 2; ++s)
+            for (int q = 1; q <= ncls; ++q)
+                r += fa->hist[(size_t)i * hs + ((size_t)k * 2 + s) * (ncls + 1) + q] *
+                     fb->hist[(size_t)j * hs + ((size_t)k * 2 + s) * (ncls + 1) + q];
+    }
+    c[0] += 1;
+    c[1] += (int64_t)fa->nint[i] * fb->nint[j];
+    c[2] += m;
+    c[3] += r;
+}
+
+extern "C" int pk_forest_pair_stats(const pk_forest *fa, const pk_forest *fb, const int32_t *pairs, int64_t npairs,
+                                    int64_t counts[4]) {
+    if (!fa || !fb || !pairs || !counts) return pk_fail(PK_ERR_INVALID, "null argument");
+    if (fa->ncls != fb->ncls) return pk_fail(PK_ERR_INVALID, "forests use different production class schemes");
+    counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    for (int64_t p = 0; p < npairs; ++p) {
+        int i = pairs[2 * p], j = pairs[2 * p + 1];
+        if (i < 0 || i >= fa->n || j < 0 || j >= fb->n) return pk_fail(PK_ERR_INVALID, "pair index out of range");
+        pair_work(fa, i, fb, j, counts);
+    }
+    return PK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launch
+// ---------------------------------------------------------------------------------------------------
+template <typename T, bool CSMEM, int NT>
+static cudaError_t launch_t(const DpArgs &args, int grid, int smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(pk_dp_kernel<T, CSMEM, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    pk_dp_kernel<T, CSMEM, NT><<<grid, NT, smem, stream>>>(args);
+    return cudaGetLastError();
+}
+
+template <typename T, bool CSMEM, int NT>
+static cudaError_t occupancy_t(int smem, int *blocks) {
+    cudaError_t e = cudaFuncSetAttribute(pk_dp_kernel<T, CSMEM, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, pk_dp_kernel<T, CSMEM, NT>, NT, smem);
+}
+
+#define PK_DISPATCH(FN, ...)                                                                    \
+    (prec32 ? (csmem ? (nt == 128   ? FN<float, true, 128>(__VA_ARGS__)                         \
+                        : nt == 256 ? FN<float, true, 256>(__VA_ARGS__)                         \
+                        : nt == 512 ? FN<float, true, 512>(__VA_ARGS__)                         \
+                                    : FN<float, true, 1024>(__VA_ARGS__))                       \
+                     : (nt == 128   ? FN<float, false, 128>(__VA_ARGS__)                        \
+                        : nt == 256 ? FN<float, false, 256>(__VA_ARGS__)                        \
+                        : nt == 512 ? FN<float, false, 512>(__VA_ARGS__)                        \
+                                    : FN<float, false, 1024>(__VA_ARGS__)))                     \
+            : (csmem ? (nt == 128   ? FN<double, true, 128>(__VA_ARGS__)                        \
+                        : nt == 256 ? FN<double, true, 256>(__VA_ARGS__)                        \
+                        : nt == 512 ? FN<double, true, 512>(__VA_ARGS__)                        \
+                                    : FN<double, true, 1024>(__VA_ARGS__))                      \
+                     : (nt == 128   ? FN<double, false, 128>(__VA_ARGS__)                       \
+                        : nt == 256 ? FN<double, false, 256>(__VA_ARGS__)                       \
+                        : nt == 512 ? FN<double, false, 512>(__VA_ARGS__)                       \
+                                    : FN<double, false, 1024>(__VA_ARGS__))))
+
+static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpArgs args, const pk_params *p) {
+    if (fa->ctx != ctx || fb->ctx != ctx) return pk_fail(PK_ERR_INVALID, "forest belongs to another context");
+    if (fa->precision != fb->precision) return pk_fail(PK_ERR_INVALID, "forests were uploaded with different precision");
+    if (fa->ncls != fb->ncls) return pk_fail(PK_ERR_INVALID, "forests use different production class schemes");
+    if (p->precision != 0 && p->precision != fa->precision)
+        return pk_fail(PK_ERR_INVALID, "params.precision does not match the forest's precision");
+    if (!(p->gauss != 0.0) || !std::isfinite(p->gauss) || !std::isfinite(p->decay) || !std::isfinite(p->sigma))
+        return pk_fail(PK_ERR_INVALID, "decayFactor, gaussFactor, sigma must be finite and gaussFactor non-zero");
+    if (args.total <= 0) return PK_OK;
+    const bool prec32 = fa->precision == 32;
+    const size_t w = prec32 ? 4 : 8;
+
+    args.blocksA = fa->d_blocks;
+    args.metaA = fa->d_meta;
+    args.blocksB = fb->d_blocks;
+    args.metaB = fb->d_meta;
+    args.lambda = p->decay;
+    args.neg_inv_tau = -1.0 / p->gauss;
+    args.sigma = p->sigma;
+
+    // upper bound of the compact C size over all pairs of the two forests
+    long long maxM = 1;
+    for (int c = 0; c < fa->ncls; ++c) maxM += (long long)fa->max_cnt[c] * fb->max_cnt[c];
+    const int region = (std::max(fa->max_block, fb->max_block) + 127) & ~127;
+    const int rowinfo = ((std::max(fa->max_n, fb->max_n) * 16) + 127) & ~127;
+    const long long base_smem = 2ll * region + rowinfo;
+    const long long limit = ctx->smem_optin - 1024;   // static shared memory of the kernel
+    if (base_smem > limit)
+        return pk_fail(PK_ERR_INVALID, "trees too large to stage in shared memory (" + std::to_string(base_smem) +
+                                           " bytes needed, " + std::to_string(limit) + " available)");
+    const long long c_bytes = ((maxM * (long long)w) + 127) & ~127ll;
+    bool csmem = !ctx->cfg_force_hbm && base_smem + c_bytes <= limit;
+    int nt = ctx->cfg_threads ? ctx->cfg_threads : (csmem ? 256 : 512);
+    int smem = (int)(csmem ? base_smem + c_bytes : base_smem);
+    args.tree_region = region;
+    args.rowinfo_bytes = rowinfo;
+
+    int per_sm = 1;
+    cudaError_t e = PK_DISPATCH(occupancy_t, smem, &per_sm);
+    if (e != cudaSuccess) return pk_fail(PK_ERR_CUDA, std::string("occupancy query: ") + cudaGetErrorString(e));
+    if (per_sm < 1) return pk_fail(PK_ERR_CUDA, "kernel does not fit on an SM with the requested configuration");
+    if (!csmem && ctx->cfg_ctas > 0) per_sm = std::min(per_sm, ctx->cfg_ctas);
+    if (!csmem && ctx->cfg_ctas == 0) {
+        // keep the C slabs of all resident CTAs inside L2 (~126 MB) when possible
+        long long slab_bytes = ((maxM * (long long)w) + 255) & ~255ll;
+        long long fit = (100ll << 20) / std::max(1ll, slab_bytes * ctx->sm_count);
+        per_sm = (int)std::max(1ll, std::min<long long>(per_sm, fit));
+    }
+    long long grid_ll = std::min<long long>(args.total, (long long)per_sm * ctx->sm_count);
+    int grid = (int)std::max(1ll, grid_ll);
+    if (!csmem) {
+        args.slab_elems = (((maxM * (long long)w) + 255) & ~255ll) / (long long)w;
+        int rc = ensure_scratch(ctx, (size_t)grid * (size_t)args.slab_elems * w);
+        if (rc) return rc;
+        args.scratch = ctx->d_scratch;
+    }
+    args.counter = ctx->d_counters + (ctx->counter_next++ % kCounterRing);
+    PK_CUDA(cudaMemsetAsync(args.counter, 0, sizeof(unsigned long long), ctx->stream));
+    PK_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    e = PK_DISPATCH(launch_t, args, grid, smem, ctx->stream);
+    if (e != cudaSuccess) return pk_fail(PK_ERR_CUDA, std::string("DP kernel launch: ") + cudaGetErrorString(e));
+    PK_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    ctx->ev_valid = true;
+    ctx->launches++;
+    ctx->last_path = csmem ? 0 : 1;
+    ctx->last_grid = grid;
+    ctx->last_threads = nt;
+    ctx->last_smem = smem;
+    return PK_OK;
+}
+
+extern "C" int pk_forest_kernel_pairs(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, const int32_t *d_pairs,
+                                      int32_t npairs, const pk_params *params, double *d_out_k) {
+    if (!ctx || !fa || !fb || !params || (npairs > 0 && (!d_pairs || !d_out_k)))
+        return pk_fail(PK_ERR_INVALID, "null argument");
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    DpArgs args;
+    std::memset(&args, 0, sizeof(args));
+    args.mode = 0;
+    args.pairs = reinterpret_cast<const int2 *>(d_pairs);
+    args.total = npairs;
+    args.out = d_out_k;
+    return launch_dp(ctx, fa, fb, args, params);
+}
+
+extern "C" int pk_kernel_pairs(pk_ctx *ctx, const pk_tree *const *A, int32_t nA, const pk_tree *const *B, int32_t nB,
+                               const int32_t *pairs, int32_t npairs, const pk_params *params, double *out_k) {
+    if (!ctx || !A || !B || !params || (npairs > 0 && (!pairs || !out_k))) return pk_fail(PK_ERR_INVALID, "null argument");
+    if (npairs <= 0) return PK_OK;
+    for (int32_t p = 0; p < npairs; ++p)
+        if (pairs[2 * p] < 0 || pairs[2 * p] >= nA || pairs[2 * p + 1] < 0 || pairs[2 * p + 1] >= nB)
+            return pk_fail(PK_ERR_INVALID, "pair index out of range");
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    const int prec = params->precision == 32 ? 32 : 64;
+    pk_forest *fa = nullptr, *fb = nullptr;
+    rc = pk_forest_upload(ctx, A, nA, prec, &fa);
+    if (rc) return rc;
+    const bool same = (A == B && nA == nB);
+    if (same) fb = fa;
+    else rc = pk_forest_upload(ctx, B, nB, prec, &fb);
+    if (rc == PK_OK) {
+        const size_t pb = sizeof(int32_t) * 2 * (size_t)npairs, ob = sizeof(double) * (size_t)npairs;
+        const size_t pb_al = (pb + 255) & ~(size_t)255;
+        rc = ensure_tmp(ctx, pb_al + ob);
+        if (rc == PK_OK) rc = ensure_pinned(ctx, pb_al + ob);
+        if (rc == PK_OK) {
+            unsigned char *d = static_cast<unsigned char *>(ctx->d_tmp);
+            unsigned char *h = static_cast<unsigned char *>(ctx->h_pinned);
+            std::memcpy(h, pairs, pb);
+            cudaError_t e = cudaMemcpyAsync(d, h, pb, cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) rc = pk_fail(PK_ERR_CUDA, cudaGetErrorString(e));
+            pk_params pp = *params;
+            pp.precision = prec;
+            if (rc == PK_OK)
+                rc = pk_forest_kernel_pairs(ctx, fa, fb, reinterpret_cast<int32_t *>(d), npairs, &pp,
+                                            reinterpret_cast<double *>(d + pb_al));
+            if (rc == PK_OK) {
+                e = cudaMemcpyAsync(h + pb_al, d + pb_al, ob, cudaMemcpyDeviceToHost, ctx->stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+                if (e != cudaSuccess) rc = pk_fail(PK_ERR_CUDA, std::string("pk_kernel_pairs: ") + cudaGetErrorString(e));
+                else std::memcpy(out_k, h + pb_al, ob);
+            }
+        }
+    }
+    std::string keep = rc ? std::string(pk_last_error()) : std::string();
+    if (fb && fb != fa) pk_forest_free(fb);
+    pk_forest_free(fa);
+    if (rc) pk_set_error(keep);
+    return rc;
+}
+
+extern "C" int pk_score_batch(pk_ctx *ctx, const pk_tree *obs, const pk_tree *const *sims, int32_t nsims,
+                              const pk_params *params, double *ref_denom, double *out_k, double *out_denom,
+                              double *out_khat) {
+    if (!ctx || !obs || !sims || !params || !ref_denom) return pk_fail(PK_ERR_INVALID, "null argument");
+    if (nsims < 1) return pk_fail(PK_ERR_INVALID, "no simulated trees");
+    std::vector<const pk_tree *> all((size_t)nsims + 1);
+    all[0] = obs;
+    for (int32_t s = 0; s < nsims; ++s) all[s + 1] = sims[s];
+    const bool need_ref = !(*ref_denom > 0.0);   // NaN or <= 0: compute K(obs, obs) (kamphir.py:157)
+    const int32_t np = 2 * nsims + (need_ref ? 1 : 0);
+    std::vector<int32_t> pairs(2 * (size_t)np);
+    for (int32_t s = 0; s < nsims; ++s) {
+        pairs[2 * (size_t)s] = 0;                       // k = kernel(target_tree, tree)      kamphir.py:290
+        pairs[2 * (size_t)s + 1] = s + 1;
+        pairs[2 * (size_t)(nsims + s)] = s + 1;         // tree_denom = kernel(tree, tree)    kamphir.py:291
+        pairs[2 * (size_t)(nsims + s) + 1] = s + 1;
+    }
+    if (need_ref) pairs[2 * (size_t)(2 * nsims)] = pairs[2 * (size_t)(2 * nsims) + 1] = 0;
+    std::vector<double> k((size_t)np);
+    int rc = pk_kernel_pairs(ctx, all.data(), nsims + 1, all.data(), nsims + 1, pairs.data(), np, params, k.data());
+    if (rc) return rc;
+    if (need_ref) *ref_denom = k[2 * (size_t)nsims];
+    for (int32_t s = 0; s < nsims; ++s) {
+        if (out_k) out_k[s] = k[s];
+        if (out_denom) out_denom[s] = k[(size_t)nsims + s];
+        if (out_khat)                                   // kamphir.py:300, evaluated in log space like the reference
+            out_khat[s] = std::exp(std::log(k[s]) - 0.5 * (std::log(*ref_denom) + std::log(k[(size_t)nsims + s])));
+    }
+    return PK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Gram matrix
+// ---------------------------------------------------------------------------------------------------
+static int gram_tiles(int32_t n, int32_t tile, int32_t part, int32_t nparts, std::vector<int2> *tiles, int64_t *npairs) {
+    if (n < 1 || tile < 1 || (tile & (tile - 1)) || nparts < 1 || part < 0 || part >= nparts)
+        return pk_fail(PK_ERR_INVALID, "gram: tile must be a power of two, 0 <= part < nparts");
+    const int32_t nt = (n + tile - 1) / tile;
+    int64_t t = 0, cnt = 0;
+    for (int32_t ti = 0; ti < nt; ++ti)
+        for (int32_t tj = ti; tj < nt; ++tj, ++t) {
+            if (t % nparts != part) continue;
+            if (tiles) tiles->push_back(make_int2(ti, tj));
+            const int64_t hi = std::min<int64_t>(n, (int64_t)(ti + 1) * tile) - (int64_t)ti * tile;
+            const int64_t wj = std::min<int64_t>(n, (int64_t)(tj + 1) * tile) - (int64_t)tj * tile;
+            cnt += (ti == tj) ? hi * (hi + 1) / 2 : hi * wj;
+        }
+    if (npairs) *npairs = cnt;
+    return PK_OK;
+}
+
+extern "C" int pk_gram_part_pairs(int32_t n, int32_t tile, int32_t part, int32_t nparts, int64_t *npairs) {
+    if (!npairs) return pk_fail(PK_ERR_INVALID, "null argument");
+    return gram_tiles(n, tile, part, nparts, nullptr, npairs);
+}
+
+extern "C" int pk_forest_gram_stats(const pk_forest *f, int32_t tile, int32_t part, int32_t nparts, int64_t counts[4]) {
+    if (!f || !counts) return pk_fail(PK_ERR_INVALID, "null argument");
+    std::vector<int2> tiles;
+    int rc = gram_tiles(f->n, tile, part, nparts, &tiles, nullptr);
+    if (rc) return rc;
+    counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    for (const int2 &t : tiles)
+        for (int i = t.x * tile; i < std::min(f->n, (t.x + 1) * tile); ++i)
+            for (int j = std::max(i, t.y * tile); j < std::min(f->n, (t.y + 1) * tile); ++j) pair_work(f, i, f, j, counts);
+    return PK_OK;
+}
+
+extern "C" int pk_forest_gram_part(pk_ctx *ctx, const pk_forest *f, const pk_params *params, int normalised, int32_t tile,
+                                   int32_t part, int32_t nparts, double *d_out, int64_t ld, double *d_diag) {
+    if (!ctx || !f || !params || !d_out) return pk_fail(PK_ERR_INVALID, "null argument");
+    if (normalised && !d_diag) return pk_fail(PK_ERR_INVALID, "normalised Gram needs a d_diag buffer");
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    std::vector<int2> tiles;
+    rc = gram_tiles(f->n, tile, part, nparts, &tiles, nullptr);
+    if (rc) return rc;
+    if (ld < f->n) return pk_fail(PK_ERR_INVALID, "gram: leading dimension smaller than N");
+    if (d_diag) {   // K_ii for every tree (needed by every part for the normalisation)
+        DpArgs dg;
+        std::memset(&dg, 0, sizeof(dg));
+        dg.mode = 2;
+        dg.n_trees = f->n;
+        dg.total = f->n;
+        dg.out = d_diag;
+        rc = launch_dp(ctx, f, f, dg, params);
+        if (rc) return rc;
+    }
+    if (tiles.empty()) return PK_OK;
+    const size_t tb = sizeof(int2) * tiles.size();
+    rc = ensure_tmp(ctx, tb);
+    if (rc == PK_OK) rc = ensure_pinned(ctx, tb);
+    if (rc) return rc;
+    std::memcpy(ctx->h_pinned, tiles.data(), tb);
+    PK_CUDA(cudaMemcpyAsync(ctx->d_tmp, ctx->h_pinned, tb, cudaMemcpyHostToDevice, ctx->stream));
+    int shift = 0;
+    while ((1 << shift) < tile) ++shift;
+    DpArgs args;
+    std::memset(&args, 0, sizeof(args));
+    args.mode = 1;
+    args.tiles = reinterpret_cast<const int2 *>(ctx->d_tmp);
+    args.tile_shift = shift;
+    args.n_trees = f->n;
+    args.total = (long long)tiles.size() << (2 * shift);
+    args.out = d_out;
+    args.ld = ld;
+    args.diag = normalised ? d_diag : nullptr;
+    return launch_dp(ctx, f, f, args, params);
+}
+
+extern "C" int pk_gram(pk_ctx *ctx, const pk_tree *const *trees, int32_t n, const pk_params *params, int normalised,
+                       double *out) {
+    if (!ctx || !trees || !params || !out) return pk_fail(PK_ERR_INVALID, "null argument");
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    const int prec = params->precision == 32 ? 32 : 64;
+    pk_forest *f = nullptr;
+    rc = pk_forest_upload(ctx, trees, n, prec, &f);
+    if (rc) return rc;
+    double *d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_out, sizeof(double) * ((size_t)n * n + n));
+    if (e != cudaSuccess) {
+        pk_forest_free(f);
+        return pk_fail(PK_ERR_CUDA, std::string("pk_gram: ") + cudaGetErrorString(e));
+    }
+    pk_params pp = *params;
+    pp.precision = prec;
+    const int32_t tile = n >= 1024 ? 32 : (n >= 128 ? 8 : 1);
+    rc = pk_forest_gram_part(ctx, f, &pp, normalised, tile, 0, 1, d_out, n, d_out + (size_t)n * n);
+    if (rc == PK_OK) {
+        e = cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = pk_fail(PK_ERR_CUDA, std::string("pk_gram: ") + cudaGetErrorString(e));
+    }
+    std::string keep = rc ? std::string(pk_last_error()) : std::string();
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_out);
+    pk_forest_free(f);
+    if (rc) pk_set_error(keep);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// device buffers / IPC (one result matrix on rank 0 written by all ranks over NVLink)
+// ---------------------------------------------------------------------------------------------------
+extern "C" int pk_device_alloc(pk_ctx *ctx, size_t bytes, void **d_ptr) {
+    if (!ctx || !d_ptr) return pk_fail(PK_ERR_INVALID, "null argument");
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    PK_CUDA(cudaMalloc(d_ptr, bytes));
+    return PK_OK;
+}
+extern "C" int pk_device_free(pk_ctx *ctx, void *d_ptr) {
+    if (!ctx) return pk_fail(PK_ERR_INVALID, "null argument");
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    PK_CUDA(cudaFree(d_ptr));
+    return PK_OK;
+}
+extern "C" int pk_ipc_export(pk_ctx *ctx, void *d_ptr, unsigned char handle[64]) {
+    if (!ctx || !d_ptr || !handle) return pk_fail(PK_ERR_INVALID, "null argument");
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    PK_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+    std::memcpy(handle, &h, 64);
+    return PK_OK;
+}
+extern "C" int pk_ipc_open(pk_ctx *ctx, const unsigned char handle[64], void **d_ptr) {
+    if (!ctx || !d_ptr || !handle) return pk_fail(PK_ERR_INVALID, "null argument");
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    PK_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PK_OK;
+}
+extern "C" int pk_ipc_close(pk_ctx *ctx, void *d_ptr) {
+    if (!ctx) return pk_fail(PK_ERR_INVALID, "null argument");
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    PK_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return PK_OK;
+}
+extern "C" int pk_memcpy_d2h(pk_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
+    if (!ctx) return pk_fail(PK_ERR_INVALID, "null argument");
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    PK_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PK_OK;
+}
+extern "C" int pk_memcpy_h2d(pk_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
+    if (!ctx) return pk_fail(PK_ERR_INVALID, "null argument");
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    PK_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PK_OK;
+}
+extern "C" int pk_memset_d(pk_ctx *ctx, void *d_dst, int value, size_t bytes) {
+    if (!ctx) return pk_fail(PK_ERR_INVALID, "null argument");
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    PK_CUDA(cudaMemsetAsync(d_dst, value, bytes, ctx->stream));
+    return PK_OK;
+}

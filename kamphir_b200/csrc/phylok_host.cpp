@@ -1,0 +1,682 @@
+// Host flattener: Newick text -> ladderized, rescaled, annotated, kernel-ordered SoA tree.
+//
+// Replaces, for the kernel path only, what the reference does with Bio.Phylo objects:
+//   Phylo.read / Phylo.parse            kamphir.py:112,323,373
+//   root.branch_length = 0; ladderize   kamphir.py:153-154, 279-280
+//   PhyloKernel.normalize_tree          phyloK2.py:101-130
+//   PhyloKernel.annotate_tree           phyloK2.py:132-146
+//   node heights for kcoal              kamphir.py:255-258
+// Structural parity with the reference (child order after the stable ladderize, post-order numbering,
+// pre-order summation order of total_branch_length) is tested bit-for-bit against the oracle in
+// tests/test_flatten.py.
+#include <algorithm>
+#include <atomic>
+#include <charconv>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <thread>
+
+#include "phylok_internal.h"
+
+// ---------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+void pk_set_error(const std::string &msg) { g_err = msg; }
+int pk_fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+extern "C" const char *pk_last_error(void) { return g_err.c_str(); }
+extern "C" int pk_abi_version(void) { return PK_ABI_VERSION; }
+
+// ---------------------------------------------------------------------------------------------------
+// Newick
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+struct RawTree {
+    std::vector<int32_t> parent, first, last, next, nchild;
+    std::vector<double> bl;                  // NaN = absent (Biopython: None)
+    std::vector<int32_t> name_off, name_len;
+    int32_t root = -1;
+
+    int32_t add(int32_t par) {
+        int32_t id = (int32_t)parent.size();
+        parent.push_back(par);
+        first.push_back(-1);
+        last.push_back(-1);
+        next.push_back(-1);
+        nchild.push_back(0);
+        bl.push_back(std::numeric_limits<double>::quiet_NaN());
+        name_off.push_back(0);
+        name_len.push_back(0);
+        if (par >= 0) link(par, id);
+        return id;
+    }
+    void link(int32_t par, int32_t id) {
+        parent[id] = par;
+        next[id] = -1;
+        if (first[par] < 0) first[par] = id; else next[last[par]] = id;
+        last[par] = id;
+        nchild[par]++;
+    }
+    size_t size() const { return parent.size(); }
+};
+
+inline bool is_punct(char c) {
+    return c == '(' || c == ')' || c == '[' || c == ']' || c == '\'' || c == ':' || c == ';' || c == ',';
+}
+inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v'; }
+
+// One tree from text[b, e) (no terminating ';').  Same token semantics as Biopython's Newick parser:
+// children in input order, '[...]' comments dropped, quoted labels, a ',' at top level creates a new root.
+int parse_one(const char *text, size_t b, size_t e, RawTree &t, std::string &err) {
+    t = RawTree();
+    t.parent.reserve(1024);
+    int32_t cur = t.add(-1);
+    t.root = cur;
+    long lp = 0, rp = 0;
+    bool synthetic_root = false;
+    size_t i = b;
+    while (i < e) {
+        char ch = text[i];
+        if (is_space(ch)) { ++i; continue; }
+        if (ch == '(') {
+            cur = t.add(cur);
+            ++lp; ++i;
+        } else if (ch == ',') {
+            int32_t par = t.parent[cur];
+            if (par < 0) {                 // outer parentheses missing: new root above the current clade
+                int32_t nr = t.add(-1);
+                t.link(nr, cur);
+                t.root = nr;
+                par = nr;
+                synthetic_root = true;
+            }
+            cur = t.add(par);
+            ++i;
+        } else if (ch == ')') {
+            int32_t par = t.parent[cur];
+            if (par < 0) { err = "Newick: parenthesis mismatch"; return PK_ERR_PARSE; }
+            cur = par;
+            ++rp; ++i;
+        } else if (ch == ':') {
+            size_t j = i + 1;
+            while (j < e && text[j] == ' ') ++j;
+            size_t k = j;
+            while (k < e && !is_punct(text[k]) && !is_space(text[k])) ++k;
+            size_t s = j;
+            if (s < k && text[s] == '+') ++s;
+            double v = 0.0;
+            auto res = std::from_chars(text + s, text + k, v);
+            if (s == k || res.ec != std::errc() || res.ptr != text + k) {
+                err = "Newick: bad branch length '" + std::string(text + j, k - j) + "'";
+                return PK_ERR_PARSE;
+            }
+            t.bl[cur] = v;
+            i = k;
+        } else if (ch == '\'') {
+            size_t j = i + 1;
+            while (j < e && text[j] != '\'') ++j;
+            if (j >= e) { err = "Newick: unterminated quoted label"; return PK_ERR_PARSE; }
+            t.name_off[cur] = (int32_t)(i + 1 - b);
+            t.name_len[cur] = (int32_t)(j - i - 1);
+            i = j + 1;
+        } else if (ch == '[') {
+            size_t j = i + 1;
+            while (j < e && text[j] != ']') ++j;
+            if (j >= e) { err = "Newick: unterminated comment"; return PK_ERR_PARSE; }
+            i = j + 1;
+        } else if (ch == ';') {
+            break;
+        } else if (ch == ']') {
+            err = "Newick: unexpected ']'";
+            return PK_ERR_PARSE;
+        } else {
+            size_t k = i;
+            while (k < e && !is_punct(text[k]) && !is_space(text[k])) ++k;
+            t.name_off[cur] = (int32_t)(i - b);
+            t.name_len[cur] = (int32_t)(k - i);
+            i = k;
+        }
+    }
+    if (lp != rp) { err = "Newick: number of open/close parentheses do not match"; return PK_ERR_PARSE; }
+    if (cur != t.root && !(synthetic_root && t.parent[cur] == t.root)) {
+        err = "Newick: parenthesis mismatch";
+        return PK_ERR_PARSE;
+    }
+    return PK_OK;
+}
+
+// splits a multi-tree text on ';' outside quotes / comments
+void split_trees(const char *text, size_t len, std::vector<std::pair<size_t, size_t>> &out) {
+    size_t start = 0, i = 0;
+    auto flush = [&](size_t end) {
+        size_t a = start, z = end;
+        while (a < z && is_space(text[a])) ++a;
+        while (z > a && is_space(text[z - 1])) --z;
+        if (z > a) out.emplace_back(a, z);
+    };
+    while (i < len) {
+        char ch = text[i];
+        if (ch == '\'') {
+            size_t j = i + 1;
+            while (j < len && text[j] != '\'') ++j;
+            i = (j < len) ? j + 1 : len;
+            continue;
+        }
+        if (ch == '[') {
+            size_t j = i + 1;
+            while (j < len && text[j] != ']') ++j;
+            i = (j < len) ? j + 1 : len;
+            continue;
+        }
+        if (ch == ';') {
+            flush(i);
+            start = i + 1;
+        }
+        ++i;
+    }
+    flush(len);
+}
+
+int tip_state(const char *text, const RawTree &t, int32_t v, int nstates, int &state, std::string &err) {
+    const char *p = text + t.name_off[v];
+    int len = t.name_len[v];
+    int k = len;
+    while (k > 0 && p[k - 1] != '_') --k;          // token after the last '_'  (rcolgem.py:274)
+    int val = 0;
+    auto res = std::from_chars(p + k, p + len, val);
+    if (k == len || res.ec != std::errc() || res.ptr != p + len || val < 0 || val >= nstates) {
+        err = "tip label '" + std::string(p, len) + "' does not end in _<state> with 0 <= state < " +
+              std::to_string(nstates);
+        return PK_ERR_INVALID;
+    }
+    state = val;
+    return PK_OK;
+}
+
+// RawTree -> pk_tree following kamphir's prep order.
+int flatten(const char *text, RawTree &r, int flags, int normalize, int nstates, pk_tree &out, std::string &err) {
+    const int32_t total = (int32_t)r.size();
+    const int32_t root = r.root;
+    const double NaN = std::numeric_limits<double>::quiet_NaN();
+
+    // pre-order (node, then children in order) and its reverse for bottom-up passes
+    std::vector<int32_t> pre;
+    pre.reserve(total);
+    std::vector<int32_t> stack;
+    auto preorder = [&]() {
+        pre.clear();
+        stack.clear();
+        stack.push_back(root);
+        std::vector<int32_t> kids;
+        while (!stack.empty()) {
+            int32_t v = stack.back();
+            stack.pop_back();
+            pre.push_back(v);
+            kids.clear();
+            for (int32_t c = r.first[v]; c >= 0; c = r.next[c]) kids.push_back(c);
+            for (size_t k = kids.size(); k-- > 0;) stack.push_back(kids[k]);
+        }
+    };
+    preorder();
+
+    if (flags & PK_PREP_ZERO_ROOT) r.bl[root] = 0.0;                       // kamphir.py:153,279
+
+    if (flags & PK_PREP_LADDERIZE) {                                       // kamphir.py:154,280
+        std::vector<int32_t> ntip(total, 0);
+        for (size_t k = pre.size(); k-- > 0;) {
+            int32_t v = pre[k];
+            if (r.first[v] < 0) ntip[v] = 1;
+            if (r.parent[v] >= 0) ntip[r.parent[v]] += ntip[v];
+        }
+        std::vector<int32_t> kids;
+        for (int32_t v = 0; v < total; ++v) {
+            if (r.nchild[v] < 2) continue;
+            kids.clear();
+            for (int32_t c = r.first[v]; c >= 0; c = r.next[c]) kids.push_back(c);
+            std::stable_sort(kids.begin(), kids.end(), [&](int32_t a, int32_t b) { return ntip[a] < ntip[b]; });
+            r.first[v] = kids.front();
+            r.last[v] = kids.back();
+            for (size_t k = 0; k < kids.size(); ++k) r.next[kids[k]] = (k + 1 < kids.size()) ? kids[k + 1] : -1;
+        }
+        preorder();
+    }
+
+    // un-normalised depths / node heights (kamphir.py:118-119,147-149,255-258); None counts as 0
+    {
+        std::vector<double> depth(total, 0.0);
+        double hmax = 0.0;
+        bool firstv = true;
+        for (int32_t v : pre) {
+            double b = std::isnan(r.bl[v]) ? 0.0 : r.bl[v];
+            depth[v] = (r.parent[v] >= 0 ? depth[r.parent[v]] : 0.0) + b;
+            if (firstv || depth[v] > hmax) hmax = depth[v];
+            firstv = false;
+        }
+        out.height = hmax;
+        out.heights.clear();
+        for (int32_t v : pre)
+            if (r.first[v] >= 0) out.heights.push_back(hmax - depth[v]);
+        std::sort(out.heights.begin(), out.heights.end());
+    }
+
+    // normalize_tree (phyloK2.py:101-130): every non-root branch divided by the mean / median
+    out.scale = 1.0;
+    if (normalize == PK_NORM_MEAN || normalize == PK_NORM_MEDIAN) {
+        const int32_t nbranches = total - 1;                               // :109
+        if (nbranches < 1) { err = "normalize_tree: tree has no branches"; return PK_ERR_INVALID; }
+        double scale;
+        if (normalize == PK_NORM_MEAN) {
+            double sum = 0.0;                                              // total_branch_length(): truthy lengths, pre-order
+            for (int32_t v : pre) {
+                double b = r.bl[v];
+                if (!std::isnan(b) && b != 0.0) sum = sum + b;
+            }
+            double rootbl = std::isnan(r.bl[root]) ? 0.0 : r.bl[root];     // reference: TypeError on None (phyloK2.py:113)
+            scale = (sum - rootbl) / nbranches;
+        } else {
+            std::vector<double> lens;
+            lens.reserve(nbranches);
+            for (int32_t v : pre) {
+                if (v == root) continue;
+                if (std::isnan(r.bl[v])) { err = "normalize_tree: branch without a length"; return PK_ERR_INVALID; }
+                lens.push_back(r.bl[v]);
+            }
+            std::sort(lens.begin(), lens.end());
+            int32_t half = nbranches / 2;                                  // py2 integer division, :123-127
+            scale = (nbranches % 2 == 0) ? (lens[half - 1] + lens[half]) / 2. : lens[half];
+        }
+        if (!(scale != 0.0) || !std::isfinite(scale)) {
+            err = "normalize_tree: zero or non-finite scale (reference: ZeroDivisionError)";
+            return PK_ERR_INVALID;
+        }
+        for (int32_t v = 0; v < total; ++v)
+            if (v != root && !std::isnan(r.bl[v])) r.bl[v] /= scale;
+        out.scale = scale;
+    } else if (normalize != PK_NORM_NONE) {
+        err = "unknown normalize mode";
+        return PK_ERR_INVALID;
+    }
+
+    // annotate_tree (phyloK2.py:132-146): internal nodes in post-order
+    std::vector<int32_t> post;
+    post.reserve(total);
+    {
+        // iterative post-order: children (in order) before the parent
+        std::vector<std::pair<int32_t, int32_t>> st;   // (node, next child to visit)
+        st.emplace_back(root, r.first[root]);
+        while (!st.empty()) {
+            auto &top = st.back();
+            if (top.second >= 0) {
+                int32_t c = top.second;
+                top.second = r.next[c];
+                st.emplace_back(c, r.first[c]);
+            } else {
+                post.push_back(top.first);
+                st.pop_back();
+            }
+        }
+    }
+    std::vector<int32_t> pidx(total, -1);
+    int32_t n = 0, ntips = 0;
+    for (int32_t v : post) {
+        if (r.first[v] >= 0) pidx[v] = n++; else ++ntips;
+    }
+    if (n == 0) { err = "tree has no internal node (reference: IndexError at phyloK2.py:169)"; return PK_ERR_INVALID; }
+    out.n = n;
+    out.ntips = ntips;
+    out.nstates = nstates;
+    out.ncls = nstates > 0 ? 1 + 2 * nstates + nstates * nstates : 3;
+    if (out.ncls > PK_MAX_CLASSES) { err = "too many tip states (max 7)"; return PK_ERR_INVALID; }
+    out.prod.assign(n, 0);
+    out.cls.assign(n, 0);
+    out.cidx.assign(2 * (size_t)n, -1);
+    out.bl.assign(2 * (size_t)n, NaN);
+    for (int32_t v : post) {
+        if (r.first[v] < 0) continue;
+        int32_t i = pidx[v];
+        if (r.nchild[v] != 2) {
+            err = "internal node " + std::to_string(i) + " has " + std::to_string(r.nchild[v]) +
+                  " children; the kernel is defined for strictly binary trees (reference: IndexError at phyloK2.py:185-189)";
+            return PK_ERR_INVALID;
+        }
+        int32_t kid[2] = {r.first[v], r.next[r.first[v]]};
+        int nterm = 0, st[2] = {-1, -1};
+        for (int s = 0; s < 2; ++s) {
+            int32_t c = kid[s];
+            double b = r.bl[c];
+            if (!std::isfinite(b)) {
+                err = std::isnan(b) ? "branch without a length (reference: TypeError at phyloK2.py:146)"
+                                    : "non-finite branch length";
+                return PK_ERR_INVALID;
+            }
+            out.bl[2 * (size_t)i + s] = b;
+            if (r.first[c] < 0) {
+                ++nterm;
+                if (nstates > 0) {
+                    int rc = tip_state(text, r, c, nstates, st[s], err);
+                    if (rc != PK_OK) return rc;
+                }
+            } else {
+                out.cidx[2 * (size_t)i + s] = pidx[c];
+            }
+        }
+        out.prod[i] = (uint8_t)(nterm + 1);                                 // :141-142
+        if (nstates == 0) {
+            out.cls[i] = (uint8_t)nterm;
+        } else if (nterm == 0) {
+            out.cls[i] = 0;
+        } else if (nterm == 1) {
+            int slot = st[0] >= 0 ? 0 : 1;
+            out.cls[i] = (uint8_t)(1 + slot * nstates + st[slot]);
+        } else {
+            out.cls[i] = (uint8_t)(1 + 2 * nstates + st[0] * nstates + st[1]);
+        }
+    }
+    return pk_tree_finish(out);
+}
+
+}  // namespace
+
+// levels, kernel order, per-class level table, child-class histograms
+int pk_tree_finish(pk_tree &t) {
+    const int32_t n = t.n, ncls = t.ncls;
+    t.level.assign(n, 0);
+    int32_t nlev = 1;
+    for (int32_t i = 0; i < n; ++i) {
+        int32_t lv = 0;
+        for (int s = 0; s < 2; ++s) {
+            int32_t c = t.cidx[2 * (size_t)i + s];
+            if (c >= 0) {
+                if (c >= i) return pk_fail(PK_ERR_INVALID, "child index is not below its parent in post-order");
+                lv = std::max(lv, t.level[c] + 1);
+            }
+        }
+        t.level[i] = lv;
+        nlev = std::max(nlev, lv + 1);
+        if (t.cls[i] >= ncls) return pk_fail(PK_ERR_INVALID, "class id out of range");
+    }
+    t.nlev = nlev;
+    // counting sort by (class, level); stable in post-order index
+    std::vector<int32_t> cnt((size_t)ncls * nlev + 1, 0);
+    for (int32_t i = 0; i < n; ++i) cnt[(size_t)t.cls[i] * nlev + t.level[i] + 1]++;
+    for (size_t k = 1; k < cnt.size(); ++k) cnt[k] += cnt[k - 1];
+    t.lvl.assign((size_t)ncls * (nlev + 1), 0);
+    t.cls_start.assign(ncls + 1, 0);
+    for (int32_t c = 0; c < ncls; ++c) {
+        for (int32_t l = 0; l <= nlev; ++l) t.lvl[(size_t)c * (nlev + 1) + l] = cnt[(size_t)c * nlev + l];
+        t.cls_start[c] = cnt[(size_t)c * nlev];
+    }
+    t.cls_start[ncls] = n;
+    t.order.assign(n, 0);
+    t.rank.assign(n, 0);
+    std::vector<int32_t> pos(cnt.begin(), cnt.end() - 1);
+    for (int32_t i = 0; i < n; ++i) {
+        int32_t row = pos[(size_t)t.cls[i] * nlev + t.level[i]]++;
+        t.order[row] = i;
+        t.rank[i] = row - t.cls_start[t.cls[i]];
+    }
+    t.hist.assign((size_t)ncls * 2 * (ncls + 1), 0);
+    for (int32_t i = 0; i < n; ++i)
+        for (int s = 0; s < 2; ++s) {
+            int32_t c = t.cidx[2 * (size_t)i + s];
+            int q = c < 0 ? 0 : t.cls[c] + 1;
+            t.hist[((size_t)t.cls[i] * 2 + s) * (ncls + 1) + q]++;
+        }
+    return PK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// device block packing
+// ---------------------------------------------------------------------------------------------------
+static inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+size_t pk_block_bytes(const pk_tree &t, int precision) {
+    size_t w = precision == 32 ? 4 : 8;
+    size_t b = PK_HDR_INTS * 4;
+    b += align16((size_t)(t.ncls + 1) * 4);
+    b += align16((size_t)t.ncls * (t.nlev + 1) * 4);
+    b += 2 * align16((size_t)t.n * w);
+    b += 2 * align16((size_t)t.n * 4);
+    return b;
+}
+
+void pk_block_pack(const pk_tree &t, int precision, unsigned char *dst) {
+    const size_t w = precision == 32 ? 4 : 8;
+    const size_t total = pk_block_bytes(t, precision);
+    std::memset(dst, 0, total);
+    int32_t *hdr = reinterpret_cast<int32_t *>(dst);
+    size_t off = PK_HDR_INTS * 4;
+    hdr[0] = t.n; hdr[1] = t.ncls; hdr[2] = t.nlev; hdr[3] = (int32_t)total; hdr[10] = t.ntips; hdr[11] = precision;
+    hdr[4] = (int32_t)off;
+    std::memcpy(dst + off, t.cls_start.data(), (size_t)(t.ncls + 1) * 4);
+    off += align16((size_t)(t.ncls + 1) * 4);
+    hdr[5] = (int32_t)off;
+    std::memcpy(dst + off, t.lvl.data(), t.lvl.size() * 4);
+    off += align16((size_t)t.ncls * (t.nlev + 1) * 4);
+    for (int s = 0; s < 2; ++s) {
+        hdr[6 + s] = (int32_t)off;
+        for (int32_t row = 0; row < t.n; ++row) {
+            double v = t.bl[2 * (size_t)t.order[row] + s];
+            if (w == 8) reinterpret_cast<double *>(dst + off)[row] = v;
+            else reinterpret_cast<float *>(dst + off)[row] = (float)v;
+        }
+        off += align16((size_t)t.n * w);
+    }
+    for (int s = 0; s < 2; ++s) {
+        hdr[8 + s] = (int32_t)off;
+        int32_t *code = reinterpret_cast<int32_t *>(dst + off);
+        for (int32_t row = 0; row < t.n; ++row) {
+            int32_t c = t.cidx[2 * (size_t)t.order[row] + s];
+            code[row] = c < 0 ? 0 : (((int32_t)t.cls[c] + 1) << 24) | t.rank[c];
+        }
+        off += align16((size_t)t.n * 4);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI, host part
+// ---------------------------------------------------------------------------------------------------
+extern "C" int pk_tree_from_newick(const char *text, size_t len, int prep_flags, int normalize, int n_states,
+                                   pk_tree **out) {
+    if (!text || !out) return pk_fail(PK_ERR_INVALID, "null argument");
+    if (n_states < 0) return pk_fail(PK_ERR_INVALID, "n_states < 0");
+    *out = nullptr;
+    std::vector<std::pair<size_t, size_t>> ranges;
+    split_trees(text, len, ranges);
+    if (ranges.size() != 1)
+        return pk_fail(PK_ERR_PARSE, "expected exactly one tree, found " + std::to_string(ranges.size()));
+    RawTree raw;
+    std::string err;
+    int rc = parse_one(text, ranges[0].first, ranges[0].second, raw, err);
+    if (rc != PK_OK) return pk_fail(rc, err);
+    pk_tree *t = new (std::nothrow) pk_tree();
+    if (!t) return pk_fail(PK_ERR_NOMEM, "out of memory");
+    rc = flatten(text + ranges[0].first, raw, prep_flags, normalize, n_states, *t, err);
+    if (rc != PK_OK) {
+        delete t;
+        return pk_fail(rc, err.empty() ? std::string(pk_last_error()) : err);
+    }
+    *out = t;
+    return PK_OK;
+}
+
+extern "C" int pk_trees_from_newick(const char *text, size_t len, int prep_flags, int normalize, int n_states,
+                                    int nthreads, pk_tree ***out, int32_t *n_out) {
+    if (!text || !out || !n_out) return pk_fail(PK_ERR_INVALID, "null argument");
+    *out = nullptr;
+    *n_out = 0;
+    std::vector<std::pair<size_t, size_t>> ranges;
+    split_trees(text, len, ranges);
+    const size_t nt = ranges.size();
+    pk_tree **arr = new (std::nothrow) pk_tree *[nt + 1]();
+    if (!arr) return pk_fail(PK_ERR_NOMEM, "out of memory");
+    if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
+    nthreads = (int)std::min<size_t>((size_t)nthreads, std::max<size_t>(1, nt / 8));
+    std::atomic<size_t> next{0};
+    std::atomic<int> status{PK_OK};
+    std::string first_err;
+    std::atomic<bool> have_err{false};
+    auto worker = [&]() {
+        RawTree raw;
+        std::string err;
+        for (;;) {
+            size_t k = next.fetch_add(1);
+            if (k >= nt || status.load() != PK_OK) break;
+            int rc = parse_one(text, ranges[k].first, ranges[k].second, raw, err);
+            if (rc == PK_OK) {
+                arr[k] = new (std::nothrow) pk_tree();
+                if (!arr[k]) { rc = PK_ERR_NOMEM; err = "out of memory"; }
+                else rc = flatten(text + ranges[k].first, raw, prep_flags, normalize, n_states, *arr[k], err);
+            }
+            if (rc != PK_OK) {
+                bool expected = false;
+                if (have_err.compare_exchange_strong(expected, true)) {
+                    first_err = "tree " + std::to_string(k) + ": " + (err.empty() ? std::string(pk_last_error()) : err);
+                    status.store(rc);
+                }
+                break;
+            }
+        }
+    };
+    if (nthreads <= 1) {
+        worker();
+    } else {
+        std::vector<std::thread> pool;
+        for (int i = 0; i < nthreads; ++i) pool.emplace_back(worker);
+        for (auto &th : pool) th.join();
+    }
+    if (status.load() != PK_OK) {
+        for (size_t k = 0; k < nt; ++k) delete arr[k];
+        delete[] arr;
+        return pk_fail(status.load(), first_err);
+    }
+    *out = arr;
+    *n_out = (int32_t)nt;
+    return PK_OK;
+}
+
+extern "C" void pk_tree_array_free(pk_tree **arr) { delete[] arr; }
+
+extern "C" int pk_tree_from_arrays(int32_t n_internal, const int32_t *cidx, const double *bl, const uint8_t *cls,
+                                   int32_t n_classes, pk_tree **out) {
+    if (!cidx || !bl || !out) return pk_fail(PK_ERR_INVALID, "null argument");
+    if (n_internal < 1) return pk_fail(PK_ERR_INVALID, "tree has no internal node (reference: IndexError at phyloK2.py:169)");
+    *out = nullptr;
+    pk_tree *t = new (std::nothrow) pk_tree();
+    if (!t) return pk_fail(PK_ERR_NOMEM, "out of memory");
+    t->n = n_internal;
+    t->ncls = cls ? n_classes : 3;
+    if (t->ncls < 1 || t->ncls > PK_MAX_CLASSES) {
+        delete t;
+        return pk_fail(PK_ERR_INVALID, "n_classes out of range");
+    }
+    t->nstates = cls ? -1 : 0;
+    t->cidx.assign(cidx, cidx + 2 * (size_t)n_internal);
+    t->bl.assign(bl, bl + 2 * (size_t)n_internal);
+    t->prod.assign(n_internal, 0);
+    t->cls.assign(n_internal, 0);
+    int32_t tips = 0;
+    for (int32_t i = 0; i < n_internal; ++i) {
+        int nterm = 0;
+        for (int s = 0; s < 2; ++s) {
+            int32_t c = cidx[2 * (size_t)i + s];
+            if (c < -1 || c >= n_internal) {
+                delete t;
+                return pk_fail(PK_ERR_INVALID, "child index out of range");
+            }
+            if (!std::isfinite(bl[2 * (size_t)i + s])) {
+                delete t;
+                return pk_fail(PK_ERR_INVALID, "missing or non-finite branch length");
+            }
+            if (c < 0) ++nterm;
+        }
+        tips += nterm;
+        t->prod[i] = (uint8_t)(nterm + 1);
+        t->cls[i] = cls ? cls[i] : (uint8_t)nterm;
+    }
+    t->ntips = tips;
+    int rc = pk_tree_finish(*t);
+    if (rc != PK_OK) {
+        delete t;
+        return rc;
+    }
+    *out = t;
+    return PK_OK;
+}
+
+extern "C" void pk_tree_free(pk_tree *t) { delete t; }
+
+extern "C" int pk_tree_get_info(const pk_tree *t, pk_tree_info *info) {
+    if (!t || !info) return pk_fail(PK_ERR_INVALID, "null argument");
+    info->n_internal = t->n;
+    info->n_tips = t->ntips;
+    info->n_levels = t->nlev;
+    info->n_classes = t->ncls;
+    info->n_states = t->nstates;
+    info->reserved = 0;
+    info->height = t->height;
+    info->scale = t->scale;
+    return PK_OK;
+}
+
+extern "C" int pk_tree_export(const pk_tree *t, uint8_t *prod, uint8_t *cprod, int32_t *cidx, double *bl) {
+    if (!t) return pk_fail(PK_ERR_INVALID, "null argument");
+    for (int32_t i = 0; i < t->n; ++i) {
+        if (prod) prod[i] = t->nstates != 0 ? (uint8_t)(t->cls[i] + 1) : t->prod[i];
+        for (int s = 0; s < 2; ++s) {
+            int32_t c = t->cidx[2 * (size_t)i + s];
+            if (cprod) cprod[2 * (size_t)i + s] = c < 0 ? 0 : (t->nstates != 0 ? (uint8_t)(t->cls[c] + 1) : t->prod[c]);
+            if (cidx) cidx[2 * (size_t)i + s] = c;
+            if (bl) bl[2 * (size_t)i + s] = t->bl[2 * (size_t)i + s];
+        }
+    }
+    return PK_OK;
+}
+
+extern "C" int pk_tree_node_heights(const pk_tree *t, double *heights) {
+    if (!t || !heights) return pk_fail(PK_ERR_INVALID, "null argument");
+    if ((int32_t)t->heights.size() != t->n) return pk_fail(PK_ERR_INVALID, "tree was built from arrays: no node heights");
+    std::memcpy(heights, t->heights.data(), sizeof(double) * (size_t)t->n);
+    return PK_OK;
+}
+
+extern "C" int pk_pair_counts(const pk_tree *a, const pk_tree *b, int64_t counts[3]) {
+    if (!a || !b || !counts) return pk_fail(PK_ERR_INVALID, "null argument");
+    if (a->ncls != b->ncls) return pk_fail(PK_ERR_INVALID, "trees use different production class schemes");
+    int64_t m = 0, r = 0;
+    const int ncls = a->ncls;
+    for (int c = 0; c < ncls; ++c) {
+        m += (int64_t)(a->cls_start[c + 1] - a->cls_start[c]) * (b->cls_start[c + 1] - b->cls_start[c]);
+        for (int s = 0; s < 2; ++s)
+            for (int q = 1; q <= ncls; ++q)
+                r += a->hist[((size_t)c * 2 + s) * (ncls + 1) + q] * b->hist[((size_t)c * 2 + s) * (ncls + 1) + q];
+    }
+    counts[0] = (int64_t)a->n * b->n;
+    counts[1] = m;
+    counts[2] = r;
+    return PK_OK;
+}
+
+extern "C" int pk_kcoal(const pk_tree *sim, const pk_tree *target, double *out) {
+    if (!sim || !target || !out) return pk_fail(PK_ERR_INVALID, "null argument");
+    if ((int32_t)sim->heights.size() != sim->n || (int32_t)target->heights.size() != target->n)
+        return pk_fail(PK_ERR_INVALID, "node heights unavailable (tree built from arrays)");
+    if (sim->n > target->n)
+        return pk_fail(PK_ERR_INVALID, "simulated tree has more internal nodes than the target (reference: IndexError at kamphir.py:264)");
+    double dot = 0, n1 = 0, n2 = 0;                                          // kamphir.py:260-269
+    for (int32_t k = 0; k < sim->n; ++k) {
+        double h = sim->heights[k], g = target->heights[k];
+        dot += h * g;
+        n1 += h * h;
+        n2 += g * g;
+    }
+    *out = dot / (std::sqrt(n1) * std::sqrt(n2));
+    return PK_OK;
+}

@@ -1,0 +1,53 @@
+// Internal definitions shared by the host flattener (phylok_host.cpp) and the device side (phylok_dev.cu).
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <string>
+#include <vector>
+
+#include "../../include/phylok.h"
+
+#define PK_MAX_CLASSES 64          // 1 + 2S + S*S production classes with S <= 7 tip states
+#define PK_HDR_INTS 16             // per-tree block header, 64 bytes
+
+// ---- one flattened tree (host) ---------------------------------------------------------------------
+// Post-order arrays are exactly what annotate_tree (phyloK2.py:132-146) hangs on the Clade objects.
+// "Kernel order" sorts the internal nodes by (production class, wavefront level, post-order index): with
+// that order the production-matched node pairs of a tree pair are, per class, one dense cntA x cntB
+// rectangle, and one wavefront level of the row tree is a contiguous row range of it.
+struct pk_tree {
+    int32_t n = 0;          // internal nodes
+    int32_t ntips = 0;
+    int32_t nlev = 0;       // wavefront levels (level 0 = nodes without internal children)
+    int32_t ncls = 3;
+    int32_t nstates = 0;
+    double height = 0.0;    // un-normalised max depth
+    double scale = 1.0;     // normalisation divisor
+    std::vector<uint8_t> prod;      // [n]   production, 1..3
+    std::vector<uint8_t> cls;       // [n]   class id in [0, ncls)  (unlabelled: prod - 1)
+    std::vector<int32_t> cidx;      // [2n]  post-order index of internal child, -1 = tip
+    std::vector<double> bl;         // [2n]  child branch lengths (after normalisation)
+    std::vector<int32_t> level;     // [n]
+    std::vector<int32_t> order;     // [n]   kernel row -> post-order index
+    std::vector<int32_t> rank;      // [n]   post-order index -> rank within its class
+    std::vector<int32_t> cls_start; // [ncls + 1]
+    std::vector<int32_t> lvl;       // [ncls * (nlev + 1)]  absolute first kernel row of level L in class c
+    std::vector<int64_t> hist;      // [ncls * 2 * (ncls + 1)]  nodes of class c whose slot-s child has class q (0 = tip)
+    std::vector<double> heights;    // [n]   ascending node heights, un-normalised
+};
+
+// Device block of one tree (16-byte aligned, staged into shared memory with one bulk copy):
+//   int32 hdr[16]   : 0 n | 1 ncls | 2 nlev | 3 block bytes | 4 off cls_start | 5 off lvl | 6 off bl0 | 7 off bl1 |
+//                     8 off code0 | 9 off code1 | 10 ntips | 11 precision            (offsets in bytes from block start)
+//   int32 cls_start[ncls + 1]
+//   int32 lvl[ncls][nlev + 1]
+//   real  bl0[n], bl1[n]          (real = double or float; kernel order)
+//   int32 code0[n], code1[n]      (child: (class + 1) << 24 | rank within class;  0 = tip)
+size_t pk_block_bytes(const pk_tree &t, int precision);
+void pk_block_pack(const pk_tree &t, int precision, unsigned char *dst);
+
+void pk_set_error(const std::string &msg);
+int pk_fail(int code, const std::string &msg);
+
+// finishes a tree whose post-order arrays (prod/cls/cidx/bl, n, ncls) are filled: levels, kernel order, histograms
+int pk_tree_finish(pk_tree &t);

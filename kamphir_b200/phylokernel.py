@@ -1,0 +1,474 @@
+"""`PhyloKernel`: host-side mirror of the reference class (``/root/reference/phyloK2.py:9-236``) over libphylok.so.
+
+Same constructor keywords, attributes and methods as the reference, so ``kamphir.py`` (``class Kamphir(PhyloKernel)``,
+``kamphir.py:34,54``; calls at ``:155-157`` and ``:281-291``) keeps working through a one-line
+``phyloK2.py`` stub.  The arithmetic runs on the GPU through the C ABI in ``include/phylok.h``;
+nothing here computes a kernel value on the CPU and nothing imports ``oracle/``.
+
+Additive, batched entry points (one launch for many tree pairs):
+    flatten / flatten_many    Newick text or Bio.Phylo-like tree -> FlatTree (C++ flattener)
+    kernel_batch              K for a list of pairs / all pairs of two lists
+    score_batch               kamphir.py:288-306 for one target and nreps simulated trees, incl. kcoal
+    gram                      all-pairs matrix (raw or normalised)
+"""
+import ctypes
+import math
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import PK_NORM, PK_PREP_KAMPHIR, PK_PREP_LADDERIZE, PK_PREP_ZERO_ROOT, check, pk_params, pk_tree_info
+
+__all__ = ["PhyloKernel", "FlatTree", "Context", "get_context"]
+
+
+# ---------------------------------------------------------------------------------------------------
+# handles
+# ---------------------------------------------------------------------------------------------------
+class FlatTree(object):
+    """Owner of one ``pk_tree*``: a tree flattened to post-order SoA arrays (annotate_tree, phyloK2.py:132-146)."""
+
+    def __init__(self, handle, recipe):
+        self._h = ctypes.c_void_p(handle)
+        self._recipe = recipe
+        info = pk_tree_info()
+        check(_lib.lib().pk_tree_get_info(self._h, ctypes.byref(info)))
+        self.n_internal, self.n_tips, self.n_levels = info.n_internal, info.n_tips, info.n_levels
+        self.n_classes, self.n_states = info.n_classes, info.n_states
+        self.height, self.scale = info.height, info.scale
+
+    # -- constructors --------------------------------------------------------------------------------
+    @classmethod
+    def from_newick(cls, text, prep=PK_PREP_KAMPHIR, normalize="mean", n_states=0):
+        if isinstance(text, str):
+            text = text.encode("utf-8")
+        out = ctypes.c_void_p()
+        check(_lib.lib().pk_tree_from_newick(text, len(text), int(prep), PK_NORM[normalize], int(n_states),
+                                             ctypes.byref(out)))
+        return cls(out.value, ("newick", text, int(prep), normalize, int(n_states)))
+
+    @classmethod
+    def many_from_newick(cls, text, prep=PK_PREP_KAMPHIR, normalize="mean", n_states=0, nthreads=0):
+        """All trees of a multi-tree Newick text (``Phylo.parse``, kamphir.py:112), flattened by worker threads."""
+        if isinstance(text, str):
+            text = text.encode("utf-8")
+        arr = ctypes.POINTER(ctypes.c_void_p)()
+        n = ctypes.c_int32()
+        check(_lib.lib().pk_trees_from_newick(text, len(text), int(prep), PK_NORM[normalize], int(n_states),
+                                              int(nthreads), ctypes.byref(arr), ctypes.byref(n)))
+        try:
+            return [cls(arr[i], ("handle",)) for i in range(n.value)]
+        finally:
+            _lib.lib().pk_tree_array_free(arr)
+
+    @classmethod
+    def from_arrays(cls, cidx, bl, classes=None, n_classes=3):
+        cidx = np.ascontiguousarray(cidx, dtype=np.int32).reshape(-1)
+        bl = np.ascontiguousarray(bl, dtype=np.float64).reshape(-1)
+        if cidx.size != bl.size or cidx.size % 2:
+            raise ValueError("cidx and bl must both have 2 entries per internal node")
+        c = None
+        if classes is not None:
+            c = np.ascontiguousarray(classes, dtype=np.uint8)
+        out = ctypes.c_void_p()
+        check(_lib.lib().pk_tree_from_arrays(cidx.size // 2, cidx.ctypes.data, bl.ctypes.data,
+                                             c.ctypes.data if c is not None else None, int(n_classes),
+                                             ctypes.byref(out)))
+        return cls(out.value, ("arrays", cidx, bl, c, int(n_classes)))
+
+    # -- queries --------------------------------------------------------------------------------------
+    def export(self):
+        """(prod[n], cprod[n,2], cidx[n,2], bl[n,2]) in post-order, as annotate_tree defines them."""
+        n = self.n_internal
+        prod = np.empty(n, np.uint8)
+        cprod = np.empty((n, 2), np.uint8)
+        cidx = np.empty((n, 2), np.int32)
+        bl = np.empty((n, 2), np.float64)
+        check(_lib.lib().pk_tree_export(self._h, prod.ctypes.data, cprod.ctypes.data, cidx.ctypes.data, bl.ctypes.data))
+        return prod, cprod, cidx, bl
+
+    def node_heights(self):
+        h = np.empty(self.n_internal, np.float64)
+        check(_lib.lib().pk_tree_node_heights(self._h, h.ctypes.data))
+        return h
+
+    def pair_counts(self, other):
+        c = (ctypes.c_int64 * 3)()
+        check(_lib.lib().pk_pair_counts(self._h, other._h, c))
+        return int(c[0]), int(c[1]), int(c[2])
+
+    def kcoal(self, target):
+        out = ctypes.c_double()
+        check(_lib.lib().pk_kcoal(self._h, target._h, ctypes.byref(out)))
+        return out.value
+
+    # -- lifetime / pickling (Kamphir dill-pickles itself into Pool workers, kamphir.py:27-32) ------------
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None and h.value:
+            try:
+                _lib.lib().pk_tree_free(h)
+            except Exception:
+                pass
+
+    def __reduce__(self):
+        r = self._recipe
+        if r[0] == "newick":
+            return (_rebuild_newick, r[1:])
+        prod, cprod, cidx, bl = self.export()
+        if self.n_states != 0:
+            return (_rebuild_arrays, (cidx, bl, prod - 1, self.n_classes))
+        return (_rebuild_arrays, (cidx, bl, None, 3))
+
+
+def _rebuild_newick(text, prep, normalize, n_states):
+    return FlatTree.from_newick(text, prep, normalize, n_states)
+
+
+def _rebuild_arrays(cidx, bl, classes, n_classes):
+    return FlatTree.from_arrays(cidx, bl, classes, n_classes)
+
+
+class Context(object):
+    """One ``pk_ctx*`` (GPU + stream + scratch).  Created lazily, per process (never before a fork, kamphir.py:638)."""
+
+    def __init__(self, device=0):
+        self.device = int(device)
+        self.pid = os.getpid()
+        out = ctypes.c_void_p()
+        check(_lib.lib().pk_ctx_create(self.device, ctypes.byref(out)))
+        self._h = out
+        threads = int(os.environ.get("PK_THREADS", "0"))
+        ctas = int(os.environ.get("PK_CTAS", "0"))
+        force = int(os.environ.get("PK_FORCE_HBM", "0"))
+        if threads or ctas or force:
+            self.configure(threads, ctas, force)
+
+    def configure(self, threads=0, ctas_per_sm=0, force_hbm=0):
+        check(_lib.lib().pk_ctx_configure(self._h, int(threads), int(ctas_per_sm), int(force_hbm)))
+
+    def set_stream(self, cuda_stream):
+        check(_lib.lib().pk_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def sync(self):
+        check(_lib.lib().pk_ctx_sync(self._h))
+
+    def last_stats(self):
+        ms, launches, path = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int32()
+        cfg = (ctypes.c_int32 * 3)()
+        check(_lib.lib().pk_ctx_last_stats(self._h, ctypes.byref(ms), ctypes.byref(launches), ctypes.byref(path), cfg))
+        return dict(ms=ms.value, launches=launches.value, path="smem" if path.value == 0 else "hbm",
+                    grid=cfg[0], threads=cfg[1], smem_bytes=cfg[2])
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None and h.value and self.pid == os.getpid():
+            _lib.lib().pk_ctx_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Forest(object):
+    """Device-resident packed SoA of a set of FlatTrees (``pk_forest*``)."""
+
+    def __init__(self, ctx, trees, precision=64):
+        self.ctx = ctx
+        self.trees = list(trees)
+        self.n = len(self.trees)
+        self.precision = int(precision)
+        arr = (ctypes.c_void_p * self.n)(*[t._h for t in self.trees])
+        out = ctypes.c_void_p()
+        check(_lib.lib().pk_forest_upload(ctx._h, arr, self.n, self.precision, ctypes.byref(out)))
+        self._h = out
+
+    def nbytes(self):
+        b = ctypes.c_int64()
+        check(_lib.lib().pk_forest_bytes(self._h, ctypes.byref(b)))
+        return b.value
+
+    def gram_stats(self, tile, part=0, nparts=1):
+        c = (ctypes.c_int64 * 4)()
+        check(_lib.lib().pk_forest_gram_stats(self._h, int(tile), int(part), int(nparts), c))
+        return dict(dps=int(c[0]), node_pairs=int(c[1]), cells=int(c[2]), child_reads=int(c[3]))
+
+    def pair_stats(self, other, pairs):
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        c = (ctypes.c_int64 * 4)()
+        check(_lib.lib().pk_forest_pair_stats(self._h, other._h, pairs.ctypes.data, pairs.shape[0], c))
+        return dict(dps=int(c[0]), node_pairs=int(c[1]), cells=int(c[2]), child_reads=int(c[3]))
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None and h.value and self.ctx._h is not None:
+            _lib.lib().pk_forest_free(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_CONTEXTS = {}
+
+
+def get_context(device=None):
+    """Per-process, per-device context; a forked child gets its own (lazily)."""
+    if device is None:
+        device = int(os.environ.get("PK_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    key = (os.getpid(), int(device))
+    ctx = _CONTEXTS.get(key)
+    if ctx is None:
+        ctx = Context(device)
+        _CONTEXTS[key] = ctx
+    return ctx
+
+
+def algorithmic_bytes(stats, precision=64):
+    """w*(M+R) + 32*(n1+n2) + 8 per DP, summed; node_sum = sum over DPs of (n1 + n2)."""
+    w = 8 if precision == 64 else 4
+    return w * (stats["cells"] + stats["child_reads"]) + 32 * stats.get("node_sum", 0) + 8 * stats["dps"]
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's class
+# ---------------------------------------------------------------------------------------------------
+class PhyloKernel(object):
+    """Drop-in for ``phyloK2.PhyloKernel`` (constructor: phyloK2.py:10-62; same keyword names and defaults)."""
+
+    def __init__(self,
+                 kmat=None,
+                 rotate='ladder',
+                 rotate2='none',
+                 subtree=False,
+                 normalize='mean',
+                 sigma=1,
+                 gaussFactor=1,
+                 withLengths=True,
+                 decayFactor=0.1,
+                 verbose=False,
+                 resolve_poly=False,
+                 **kwargs):
+        self.trees = []
+        self.kmat = []
+        self.is_kmat_computed = False
+        self.rotate = rotate
+        self.rotate2 = rotate2
+        self.subtree = subtree
+        self.normalize = normalize
+        self.sigma = sigma
+        self.gaussFactor = gaussFactor
+        self.withLengths = withLengths
+        self.decayFactor = decayFactor
+        self.verbose = verbose
+        self.resolve_poly = resolve_poly
+        self.pcache = {}
+        self.subtrees = {}
+        # additive knobs (not in the reference): compute precision, GPU index, tip-state count
+        self.precision = int(kwargs.pop('precision', 64))
+        self.device = kwargs.pop('device', None)
+        self.n_states = int(kwargs.pop('n_states', 0))
+        if self.precision not in (32, 64):
+            raise ValueError("precision must be 64 (fp64, 1e-9) or 32 (fp32 cells, 1e-5)")
+        if self.verbose:
+            print('creating PhyloKernel with settings')
+            print('sigma = {}'.format(self.sigma))
+            print('gaussFactor = {}'.format(self.gaussFactor))
+            print('decayFactor = {}'.format(self.decayFactor))
+
+    @property
+    def ntrees(self):
+        return len(self.trees)
+
+    # -- plumbing -------------------------------------------------------------------------------------
+    def _ctx(self):
+        return get_context(self.device)
+
+    def _params(self):
+        return pk_params(float(self.decayFactor), float(self.gaussFactor), float(self.sigma), self.precision, 0)
+
+    def __getstate__(self):
+        # dill/pickle safety (kamphir.py:27-32 pickles the bound method, i.e. the whole object): no raw pointers
+        return dict(self.__dict__)
+
+    # -- tree preparation, host side ---------------------------------------------------------------------
+    def normalize_tree(self, t, mode='median'):
+        """In-place rescale of a Bio.Phylo-like tree, phyloK2.py:101-130 (``//`` where py2 relied on int ``/``)."""
+        branches = t.get_nonterminals() + t.get_terminals()
+        nbranches = len(branches) - 1
+        targets = branches[int(not t.rooted):]
+        if mode == 'mean':
+            tree_length = t.total_branch_length() - t.root.branch_length
+            scale = tree_length / nbranches
+        elif mode == 'median':
+            lengths = sorted(b.branch_length for b in targets)
+            if nbranches % 2 == 0:
+                scale = (lengths[(nbranches // 2) - 1] + lengths[nbranches // 2]) / 2.
+            else:
+                scale = lengths[nbranches // 2]
+        else:
+            return
+        for b in targets:
+            b.branch_length /= scale
+
+    def annotate_tree(self, t):
+        """In-place annotations of phyloK2.py:132-146: production, index, bl, sqbl."""
+        for tip in t.get_terminals():
+            tip.production = 0
+        for i, node in enumerate(t.get_nonterminals(order='postorder')):
+            kids = node.clades
+            node.production = sum(1 for c in kids if c.production == 0) + 1
+            node.index = i
+            node.bl = [c.branch_length for c in kids]
+            node.sqbl = sum(b ** 2 for b in node.bl)
+
+    def flatten(self, tree, prep=0, normalize='none'):
+        """FlatTree from a FlatTree (returned as is), Newick text, or a Bio.Phylo-like tree object.
+
+        For text, ``prep``/``normalize`` select the C++ flattener's kamphir-style preparation
+        (``PK_PREP_KAMPHIR`` + ``'mean'`` = kamphir.py:279-282).  A tree *object* is taken as the caller left it
+        (the reference's ``kernel`` never re-prepares, phyloK2.py:166-172): it is walked in post-order and its
+        ``node.bl`` annotations (or, if absent, the children's branch lengths) are sent to the library.
+        """
+        if isinstance(tree, FlatTree):
+            return tree
+        if isinstance(tree, (str, bytes)):
+            return FlatTree.from_newick(tree, prep, normalize, self.n_states)
+        nodes = tree.get_nonterminals(order='postorder')
+        if not nodes:
+            raise ValueError("tree has no internal node (reference: IndexError at phyloK2.py:169)")
+        if not hasattr(nodes[0], 'production'):          # phyloK2.py:169-172
+            self.annotate_tree(tree)
+        index = {id(nd): i for i, nd in enumerate(nodes)}
+        cidx = np.empty((len(nodes), 2), np.int32)
+        bl = np.empty((len(nodes), 2), np.float64)
+        for i, nd in enumerate(nodes):
+            kids = nd.clades
+            if len(kids) != 2:
+                raise ValueError("internal node %d has %d children; the kernel is defined for strictly binary trees "
+                                 "(reference: IndexError at phyloK2.py:185-189)" % (i, len(kids)))
+            lens = getattr(nd, 'bl', None)
+            if lens is None:
+                lens = [c.branch_length for c in kids]
+            for s in (0, 1):
+                cidx[i, s] = index.get(id(kids[s]), -1) if kids[s].clades else -1
+                if lens[s] is None:
+                    raise ValueError("branch without a length (reference: TypeError at phyloK2.py:146)")
+                bl[i, s] = lens[s]
+        return FlatTree.from_arrays(cidx, bl)
+
+    def flatten_many(self, newick_text, prep=PK_PREP_KAMPHIR, normalize=None, nthreads=0):
+        """Multi-tree Newick text -> list of FlatTree, prepared like kamphir.py:279-282 by default."""
+        return FlatTree.many_from_newick(newick_text, prep, self.normalize if normalize is None else normalize,
+                                         self.n_states, nthreads)
+
+    # -- the kernel ---------------------------------------------------------------------------------------
+    def kernel(self, t1, t2, myrank=None, nprocs=None, output=None):
+        """K(t1, t2), phyloK2.py:158-209, evaluated on the GPU.
+
+        ``myrank``/``nprocs`` select the reference's row-striped mode, which is wrong by its own FIXME
+        (phyloK2.py:223).  Here rank 0 (or None) returns the full K and every other rank 0.0, so the sum that
+        ``kernel_parallel`` takes over ranks is the correct value.
+        """
+        if myrank is not None and nprocs and myrank % nprocs != 0:
+            k = 0.0
+        else:
+            k = float(self.kernel_batch([t1], [t2], pairs=[(0, 0)])[0])
+        if output is None:
+            return k
+        output.put(k)
+
+    def kernel_parallel(self, t1, t2, nthreads):
+        """phyloK2.py:211-236 without the processes: one GPU launch already uses the whole device."""
+        return self.kernel(t1, t2)
+
+    def kernel_batch(self, trees_a, trees_b=None, pairs=None):
+        """K for many pairs in one launch.  ``pairs`` = [(ia, ib), ...] -> vector; None -> len(a) x len(b) matrix."""
+        fa = [self.flatten(t) for t in trees_a]
+        same = trees_b is None
+        fb = fa if same else [self.flatten(t) for t in trees_b]
+        if pairs is None:
+            pr = np.stack(np.meshgrid(np.arange(len(fa)), np.arange(len(fb)), indexing='ij'), -1).reshape(-1, 2)
+        else:
+            pr = np.asarray(pairs).reshape(-1, 2)
+        pr = np.ascontiguousarray(pr, dtype=np.int32)
+        out = np.empty(pr.shape[0], np.float64)
+        if pr.shape[0] == 0:
+            return out
+        arr_a = (ctypes.c_void_p * len(fa))(*[t._h for t in fa])
+        arr_b = arr_a if same else (ctypes.c_void_p * len(fb))(*[t._h for t in fb])
+        p = self._params()
+        check(_lib.lib().pk_kernel_pairs(self._ctx()._h, arr_a, len(fa), arr_b, len(fb), pr.ctypes.data, pr.shape[0],
+                                         ctypes.byref(p), out.ctypes.data))
+        return out if pairs is not None else out.reshape(len(fa), len(fb))
+
+    def score_batch(self, obs, sims, ref_denom=None, kadj=None, use_kcoal=False):
+        """One ABC proposal's scores (kamphir.py:288-306, 434-450) for a target tree and its simulated replicates.
+
+        Returns a dict with ``k``, ``denom``, ``knorm`` (arrays), ``ref_denom`` and, with ``use_kcoal``,
+        ``kcoal`` and ``score = knorm * kcoal**kadj`` and their mean (``mean_score``).
+        """
+        fo = self.flatten(obs, PK_PREP_KAMPHIR, self.normalize)
+        fs = [self.flatten(s, PK_PREP_KAMPHIR, self.normalize) for s in sims]
+        n = len(fs)
+        k, d, kh = np.empty(n), np.empty(n), np.empty(n)
+        ref = ctypes.c_double(float('nan') if ref_denom is None else float(ref_denom))
+        arr = (ctypes.c_void_p * n)(*[t._h for t in fs])
+        p = self._params()
+        check(_lib.lib().pk_score_batch(self._ctx()._h, fo._h, arr, n, ctypes.byref(p), ctypes.byref(ref),
+                                        k.ctypes.data, d.ctypes.data, kh.ctypes.data))
+        res = dict(k=k, denom=d, knorm=kh, ref_denom=ref.value)
+        if use_kcoal:
+            kc = np.array([t.kcoal(fo) for t in fs])
+            res['kcoal'] = kc
+            res['score'] = kh * np.power(kc, 1.0 if kadj is None else kadj)
+            res['mean_score'] = float(res['score'].sum() / n)       # kamphir.py:450
+        else:
+            res['mean_score'] = float(kh.sum() / n)
+        return res
+
+    def gram(self, trees, normalised=True):
+        """All-pairs matrix over ``trees`` (FlatTree / Newick / tree objects): raw K or K/sqrt(K_ii K_jj)."""
+        ft = [self.flatten(t, PK_PREP_KAMPHIR, self.normalize) for t in trees]
+        n = len(ft)
+        out = np.empty((n, n), np.float64)
+        arr = (ctypes.c_void_p * n)(*[t._h for t in ft])
+        p = self._params()
+        check(_lib.lib().pk_gram(self._ctx()._h, arr, n, ctypes.byref(p), 1 if normalised else 0, out.ctypes.data))
+        return out
+
+    # -- the reference's (broken) matrix surface, made to work: phyloK2.py:68-99, 148-156 -------------------
+    def load_trees_from_file(self, handle):
+        """Parse a Newick file into ``self.trees`` (FlatTrees): ladderize when ``rotate == 'ladder'``, normalise with
+        ``self.normalize``, annotate (phyloK2.py:73-93).  The reference's other rotate/gravitate/polytomy options
+        call functions that do not exist (phyloK2.py:79-91) and are rejected here."""
+        if self.rotate not in ('ladder', 'none', None) or self.rotate2 != 'none' or self.resolve_poly:
+            raise NotImplementedError("only rotate='ladder'/'none' is defined (phyloK2.py:79-91 reference undefined names)")
+        text = handle.read() if hasattr(handle, 'read') else open(handle).read()
+        prep = PK_PREP_LADDERIZE if self.rotate == 'ladder' else 0
+        norm = self.normalize if self.normalize != 'none' else 'none'
+        if norm != 'none':
+            prep |= PK_PREP_ZERO_ROOT          # root length is "meaningless" (phyloK2.py:105) and None breaks :113
+        self.trees = FlatTree.many_from_newick(text, prep, norm, self.n_states)
+        self.kmat = np.zeros((self.ntrees, self.ntrees))
+        self.is_kmat_computed = False
+        self.delta_values = {}
+
+    def compute_matrix(self):
+        """kmat[i,j] = kmat[j,i] = kernel(trees[i], trees[j]) for j >= i, raw K (phyloK2.py:148-156)."""
+        self.kmat = self.gram(self.trees, normalised=False)
+        if self.verbose:
+            for i in range(self.ntrees):
+                for j in range(i, self.ntrees):
+                    print('%d\t%d\t%f' % (i, j, self.kmat[i, j]))
+        self.is_kmat_computed = True
+
+
+def knorm(k, ref_denom, tree_denom):
+    """kamphir.py:300 (host scalar form)."""
+    return math.exp(math.log(k) - 0.5 * (math.log(ref_denom) + math.log(tree_denom)))

@@ -1,0 +1,140 @@
+"""Seeded synthetic phylogenies for tests and benchmarks (SURVEY.md 8d "Synthetic inputs").
+
+* Kingman coalescent -- the process behind ``ape::rcoal`` that made the reference's ``tests/test.tree``
+  (``tests/make_test_data.R:5-9``): n lineages; while k > 1 wait Exp(k(k-1)/2) and merge a uniform random pair.
+* Yule -- rate-1 pure birth from one lineage until n tips, then one more Exp(n) increment on the pendant edges.
+
+Trees are returned as Newick strings with 10 significant digits per branch length (what rcolgem's
+``write.tree`` emits, ``tests/unittests.py:141``), children in generation order, so every consumer (the C++
+flattener, the oracle, the reference itself) sees byte-identical input.  Multi-type tips are named
+``"<i>_<state>"`` like ``rcolgem.py:274``.
+"""
+import numpy as np
+
+__all__ = ["kingman_newick", "yule_newick", "caterpillar_newick", "balanced_newick", "tree_set"]
+
+
+def _emit(children, blen, names, root):
+    """Iterative Newick writer over arrays (children[v] = (l, r) or None)."""
+    out = []
+    stack = [(root, 0)]
+    while stack:
+        v, st = stack.pop()
+        kids = children[v]
+        if kids is None:
+            out.append(names[v])
+            if v != root:
+                out.append(":%.10g" % blen[v])
+            continue
+        if st == 0:
+            out.append("(")
+            stack.append((v, 1))
+            stack.append((kids[0], 0))
+        elif st == 1:
+            out.append(",")
+            stack.append((v, 2))
+            stack.append((kids[1], 0))
+        else:
+            out.append(")")
+            if v != root:
+                out.append(":%.10g" % blen[v])
+    out.append(";")
+    return "".join(out)
+
+
+def _tip_names(n, rng, states, prevalence):
+    if not states:
+        return ["t%d" % (i + 1) for i in range(n)]
+    p = prevalence if prevalence is not None else [1.0 / states] * states
+    st = rng.choice(states, size=n, p=p)
+    return ["%d_%d" % (i + 1, st[i]) for i in range(n)]
+
+
+def kingman_newick(n, seed, states=0, prevalence=None):
+    """Kingman coalescent tree with n tips (ultrametric)."""
+    rng = np.random.default_rng(seed)
+    total = 2 * n - 1
+    children = [None] * total
+    height = [0.0] * total
+    blen = [0.0] * total
+    names = _tip_names(n, rng, states, prevalence) + [None] * (n - 1)
+    active = list(range(n))
+    t = 0.0
+    nxt = n
+    while len(active) > 1:
+        k = len(active)
+        t += rng.exponential(2.0 / (k * (k - 1)))
+        i, j = rng.choice(k, size=2, replace=False)
+        a, b = active[i], active[j]
+        children[nxt] = (a, b)
+        height[nxt] = t
+        blen[a] = t - height[a]
+        blen[b] = t - height[b]
+        for idx in sorted((int(i), int(j)), reverse=True):
+            active.pop(idx)
+        active.append(nxt)
+        nxt += 1
+    return _emit(children, blen, names, active[0])
+
+
+def yule_newick(n, seed, states=0, prevalence=None):
+    """Yule (pure-birth, rate 1) tree with n tips."""
+    rng = np.random.default_rng(seed)
+    total = 2 * n - 1
+    children = [None] * total
+    birth = [0.0] * total
+    blen = [0.0] * total
+    root = 0
+    leaves = [0]
+    t = 0.0
+    nxt = 1
+    while len(leaves) < n:
+        k = len(leaves)
+        t += rng.exponential(1.0 / k)
+        v = leaves.pop(int(rng.integers(k)))
+        blen[v] = t - birth[v]
+        children[v] = (nxt, nxt + 1)
+        birth[nxt] = birth[nxt + 1] = t
+        leaves.extend((nxt, nxt + 1))
+        nxt += 2
+    t += rng.exponential(1.0 / n)
+    for v in leaves:
+        blen[v] = t - birth[v]
+    tipnames = _tip_names(n, rng, states, prevalence)
+    names = [None] * total
+    for i, v in enumerate(sorted(leaves)):
+        names[v] = tipnames[i]
+    return _emit(children, blen, names, root)
+
+
+def caterpillar_newick(n, seed=0):
+    """Fully unbalanced tree (worst case for the level wavefront: n-1 levels)."""
+    rng = np.random.default_rng(seed)
+    s = "(t1:%.10g,t2:%.10g)" % (rng.exponential(), rng.exponential())
+    parts = [s]
+    for i in range(3, n + 1):
+        parts.insert(0, "(")
+        parts.append(":%.10g,t%d:%.10g)" % (rng.exponential(), i, rng.exponential()))
+    return "".join(parts) + ";"
+
+
+def balanced_newick(depth, seed=0):
+    """Perfectly balanced tree with 2**depth tips."""
+    rng = np.random.default_rng(seed)
+    level = ["t%d" % (i + 1) for i in range(2 ** depth)]
+    while len(level) > 1:
+        level = ["(%s:%.10g,%s:%.10g)" % (level[i], rng.exponential(), level[i + 1], rng.exponential())
+                 for i in range(0, len(level), 2)]
+    return level[0] + ";"
+
+
+def tree_set(n_trees, n_tips, base_seed, kind="mixed", states=0, prevalence=None):
+    """n_trees Newick strings; kind in {'kingman','yule','mixed'} (mixed = first half Kingman, rest Yule)."""
+    out = []
+    for i in range(n_trees):
+        seed = base_seed + i
+        if kind == "kingman" or (kind == "mixed" and i < (n_trees + 1) // 2):
+            out.append(kingman_newick(n_tips, seed, states, prevalence))
+        else:
+            out.append(yule_newick(n_tips, seed, states, prevalence))
+    return out

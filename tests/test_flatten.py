@@ -1,0 +1,152 @@
+"""C++ flattener (pk_tree_from_newick & co, host only) against the oracle's annotated trees: exact equality.
+
+The oracle side is the Bio.Phylo stand-in + the restated prep (kamphir.py:279-282, phyloK2.py:101-146).  No GPU.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, PREP, case_newick
+from kamphir_b200 import FlatTree, PhyloKernel, synth
+from oracle import phylok_oracle as po
+
+
+def oracle_arrays(nwk, prep):
+    f = po.prepare(po.read_newick(nwk), prep)
+    return (np.array(f.prod, np.uint8), np.array(f.cprod, np.uint8), np.array(f.cidx, np.int32),
+            np.array(f.bl, np.float64))
+
+
+def assert_same(nwk, prep):
+    flags, norm = PREP[prep]
+    ft = FlatTree.from_newick(nwk, flags, norm)
+    prod, cprod, cidx, bl = ft.export()
+    o_prod, o_cprod, o_cidx, o_bl = oracle_arrays(nwk, prep)
+    assert np.array_equal(prod, o_prod)
+    assert np.array_equal(cprod, o_cprod)
+    assert np.array_equal(cidx, o_cidx)
+    assert np.array_equal(bl, o_bl)          # bit-exact, including the mean/median rescale
+    return ft
+
+
+def test_kat_trees_flatten_exactly(kat):
+    seen = set()
+    for c in kat["cases"]:
+        for side in ("a", "b"):
+            nwk = case_newick(c[side])
+            key = (hash(nwk), c["prep"])
+            if key in seen:
+                continue
+            seen.add(key)
+            ft = assert_same(nwk, c["prep"])
+            assert ft.n_internal == c["n_internal"][0 if side == "a" else 1]
+
+
+@pytest.mark.parametrize("prep", ["raw", "kamphir:mean", "kamphir:median", "ladder:none"])
+def test_synthetic_trees_flatten_exactly(prep):
+    for nwk in (synth.tree_set(6, 37, 100, "mixed") + [synth.caterpillar_newick(30, 1), synth.balanced_newick(5, 2),
+                                                       "(a:1,b:2);", "((a:1,b:2):0.5,c:3);"]):
+        assert_same(nwk, prep)
+
+
+def test_ladderize_is_stable_on_ties():
+    # both children of the root have 2 tips: input order must be kept (Biopython: list.sort is stable)
+    nwk = "((c:3,d:4):1,(a:1,b:2):2);"
+    ft = FlatTree.from_newick(nwk, 2, "none")
+    _, _, _, bl = ft.export()
+    assert bl[0].tolist() == [3.0, 4.0] and bl[1].tolist() == [1.0, 2.0] and bl[2].tolist() == [1.0, 2.0]
+    # and a real reordering: the single tip moves in front of the cherry
+    ft = FlatTree.from_newick("((a:1,b:2):5,c:3);", 2, "none")
+    _, cprod, cidx, bl = ft.export()
+    assert bl[1].tolist() == [3.0, 5.0] and cidx[1].tolist() == [-1, 0] and cprod[1].tolist() == [0, 3]
+
+
+def test_node_heights_and_kcoal_match_oracle():
+    a, b = synth.kingman_newick(40, 1), synth.yule_newick(40, 2)
+    fa, fb = FlatTree.from_newick(a), FlatTree.from_newick(b)
+    ha = po.node_heights(po.read_newick(a))
+    assert abs(fa.height - ha[0]) < 1e-15 * max(1, ha[0])
+    np.testing.assert_allclose(fa.node_heights(), ha[1], rtol=1e-14, atol=1e-15)
+    kc = po.kcoal(po.node_heights(po.read_newick(b))[1], ha[1])
+    assert abs(fb.kcoal(fa) - kc) < 1e-14
+
+
+def test_pair_counts_match_oracle():
+    a, b = synth.kingman_newick(60, 7), synth.yule_newick(45, 8)
+    fa, fb = FlatTree.from_newick(a), FlatTree.from_newick(b)
+    assert fa.pair_counts(fb) == po.pair_counts(po.prep_kamphir(po.read_newick(a)), po.prep_kamphir(po.read_newick(b)))
+
+
+def test_newick_dialect():
+    base = FlatTree.from_newick("((A:1,B:2):3,C:4);", 0, "none").export()
+    for text in ["(('A x':1,B:2)lbl:3,C:4)root;", "((A:1,B:2)[&c=1]:3,C:4.0E0);", " ( ( A : 1 , B :2):3,\nC:4 ) ;\n",
+                 "((A:1.0,B:+2):0.3e1,C:4)99;", "(A:1,B:2):3,C:4;"]:
+        got = FlatTree.from_newick(text, 0, "none").export()
+        for x, y in zip(base, got):
+            assert np.array_equal(x, y), text
+
+
+def test_multi_tree_text_matches_single(kat):
+    text = open(os.path.join(GOLDEN, "trees", "test.tree")).read()
+    many = FlatTree.many_from_newick(text, 3, "mean", 0, 2)
+    assert len(many) == 2
+    for ft, nwk in zip(many, po._split_trees_text(text)):
+        one = FlatTree.from_newick(nwk, 3, "mean")
+        for x, y in zip(ft.export(), one.export()):
+            assert np.array_equal(x, y)
+    big = "\n".join(synth.tree_set(64, 20, 5))
+    assert len(FlatTree.many_from_newick(big, 3, "mean", 0, 4)) == 64
+
+
+@pytest.mark.parametrize("text,exc", [
+    ("((a:1,b:2,c:3):1,d:1);", ValueError),        # polytomy          (reference: IndexError / partial)
+    ("((a:1):1,d:1);", ValueError),                # unary node        (reference: IndexError phyloK2.py:188)
+    ("a:1;", ValueError),                          # single tip        (reference: IndexError phyloK2.py:169)
+    ("((a:1,b:2):1,d);", ValueError),              # missing length    (reference: TypeError phyloK2.py:146)
+    ("((a:1,b:2):1,d:1;", ValueError),             # unbalanced parentheses
+    ("((a:1,b:x):1,d:1);", ValueError),            # bad number
+    ("((a:0,b:0):0,d:0);", ValueError),            # mean normalisation of an all-zero tree: ZeroDivisionError
+    ("", ValueError),
+])
+def test_bad_trees_raise(text, exc):
+    with pytest.raises(exc):
+        FlatTree.from_newick(text, 3, "mean")
+
+
+def test_tree_objects_and_python_prep_match_reference_semantics():
+    """PhyloKernel.normalize_tree / annotate_tree on Bio.Phylo-like objects == oracle; flatten(object) == flatten(text)."""
+    pk = PhyloKernel(decayFactor=0.2, gaussFactor=2.0)
+    nwk = synth.kingman_newick(25, 9)
+    for mode in ("mean", "median"):
+        t = po.read_newick(nwk)
+        t.root.branch_length = 0.
+        t.ladderize()
+        pk.normalize_tree(t, mode)
+        pk.annotate_tree(t)
+        o = po.prep_kamphir(po.read_newick(nwk), mode)
+        nodes = t.get_nonterminals(order="postorder")
+        assert [n.production for n in nodes] == o.prod and [n.bl for n in nodes] == o.bl
+        assert [n.index for n in nodes] == list(range(len(nodes))) and [n.sqbl for n in nodes] == o.sqbl
+        ft = pk.flatten(t)
+        ref = FlatTree.from_newick(nwk, 3, mode)
+        for x, y in zip(ft.export(), ref.export()):
+            assert np.array_equal(x, y)
+
+
+def test_labelled_classes():
+    nwk = synth.kingman_newick(30, 4, states=2)
+    ft = FlatTree.from_newick(nwk, 3, "mean", 2)
+    assert ft.n_classes == 1 + 4 + 4 and ft.n_states == 2
+    with pytest.raises(ValueError):
+        FlatTree.from_newick(synth.kingman_newick(10, 4), 3, "mean", 2)      # labels without _<state>
+
+
+def test_flat_tree_pickles():
+    import pickle
+    ft = FlatTree.from_newick(synth.kingman_newick(12, 3))
+    for clone in (pickle.loads(pickle.dumps(ft)), pickle.loads(pickle.dumps(FlatTree.from_arrays(*ft.export()[2:])))):
+        for x, y in zip(ft.export(), clone.export()):
+            assert np.array_equal(x, y)
+    pk = pickle.loads(pickle.dumps(PhyloKernel(decayFactor=0.3, precision=32)))
+    assert pk.decayFactor == 0.3 and pk.precision == 32
