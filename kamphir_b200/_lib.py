@@ -3,7 +3,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libphylok.so")
+LIB_PATH = os.environ.get("PK_LIB", os.path.join(_HERE, "libphylok.so"))   # PK_LIB: kernel-variant experiments
 
 PK_OK = 0
 PK_ERR_INVALID, PK_ERR_PARSE, PK_ERR_CUDA, PK_ERR_NOMEM, PK_ERR_NODEVICE = -1, -2, -3, -4, -5

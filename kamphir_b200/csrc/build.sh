@@ -3,7 +3,7 @@
 set -euo pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-OUT=../libphylok.so
+OUT=${PK_OUT:-../libphylok.so}
 FLAGS="-O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-O3,-ffp-contract=off,-Wall,-pthread"
-$NVCC $FLAGS ${PK_PTXAS_V:+-Xptxas -v} -shared -o $OUT phylok_host.cpp phylok_dev.cu -lpthread
+$NVCC $FLAGS ${PK_DEFS:-} ${PK_PTXAS_V:+-Xptxas -v} -shared -o $OUT phylok_host.cpp phylok_dev.cu -lpthread
 echo "built $(realpath $OUT)"

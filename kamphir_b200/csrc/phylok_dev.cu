@@ -58,6 +58,7 @@ struct DpArgs {
     unsigned long long *counter;    // work counter
     int tree_region;                // bytes reserved per staged tree block in shared memory
     int rowinfo_bytes;
+    double exp_tab[64];             // lambda * 2^(j/64), j = 0..63 (fp64 Gaussian)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -91,8 +92,71 @@ __device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity) {
     } while (!done);
 }
 
-__device__ __forceinline__ double pk_exp(double x) { return exp(x); }
-__device__ __forceinline__ float pk_exp(float x) { return __expf(x); }
+// ---------------------------------------------------------------------------------------------------
+// lambda * exp(x) for x <= 0, U independent values at a time
+// ---------------------------------------------------------------------------------------------------
+// fp64: x = (k/64) ln2 + r, |r| <= ln2/128; lambda*exp(x) = tab[k & 63] * 2^(k >> 6) * p(r) with tab[j] = lambda * 2^(j/64)
+// (64 doubles in shared memory, filled by the host in fp64) and p the degree-5 Taylor polynomial (remainder r^6/720
+// < 3.5e-17; measured max relative error 4e-16).  10 fp64-pipe instructions instead of the ~17 of the generic exp();
+// below x = -700 the result is ~2^-1022 (true value < 1e-304).  The U chains are written stage by stage so the
+// scheduler interleaves them (a single DFMA chain leaves the fp64 pipe idle most of the time).
+#define PK_EXP_TAB 64
+template <int U>
+__device__ __forceinline__ void pk_gauss(const double (&x)[U], double (&out)[U], const double *tab, double /*lambda*/) {
+    double t[U], r[U], q[U];
+    int k[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) t[u] = fma(x[u], 9.23324826168936567683e+01 /* 64/ln2 */, 6755399441055744.0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        k[u] = __double2loint(t[u]);
+        t[u] -= 6755399441055744.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) r[u] = fma(t[u], -0x1.62e42fee00000p-7 /* (ln2/64) high 32 bits: exact product */, x[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) r[u] = fma(t[u], -0x1.a39ef35793c76p-39 /* (ln2/64) low part */, r[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) q[u] = fma(r[u], 8.3333333333333332e-03, 4.1666666666666664e-02);
+#pragma unroll
+    for (int u = 0; u < U; ++u) q[u] = fma(q[u], r[u], 1.6666666666666666e-01);
+#pragma unroll
+    for (int u = 0; u < U; ++u) q[u] = fma(q[u], r[u], 0.5);
+#pragma unroll
+    for (int u = 0; u < U; ++u) q[u] = fma(q[u], r[u], 1.0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) q[u] = fma(q[u], r[u], 1.0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        // x < -700 (hi word of x, as unsigned, beyond that of -700.0): pin k so the scale below stays a valid exponent
+        const int kk = (unsigned)__double2hiint(x[u]) >= 0xC085E000u ? -1022 * 64 : k[u];
+        const double p2 = __hiloint2double(__double2hiint(q[u]) + ((kk >> 6) << 20), __double2loint(q[u]));
+        out[u] = p2 * tab[kk & (PK_EXP_TAB - 1)];
+    }
+}
+template <int U>
+__device__ __forceinline__ void pk_gauss(const float (&x)[U], float (&out)[U], const double *, float lambda) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) out[u] = lambda * __expf(x[u]);
+}
+
+// integer division of small non-negative ints through fp32 (exact while a < 2^22 and the quotient's fractional part
+// stays away from 0/1 by 0.5/b, which the +0.5 guarantees); the kernel's uniform per-level bookkeeping uses it
+__device__ __forceinline__ int pk_div(int a, int b) { return __float2int_rz(__fdividef((float)a + 0.5f, (float)b)); }
+
+// per row of the row tree: branch lengths and, per child slot, the child's class + 1 (0 = tip) and the offset of the
+// child's row in the compact C layout
+template <typename T>
+struct __align__(16) RowRec {
+    T a0, a1;
+    int q0, off0, q1, off1;
+    char pad[32 - 2 * sizeof(T) - 16];
+};
+template <>
+struct __align__(16) RowRec<double> {
+    double a0, a1;
+    int q0, off0, q1, off1;
+};
 
 // ---------------------------------------------------------------------------------------------------
 // the DP kernel
@@ -100,21 +164,27 @@ __device__ __forceinline__ float pk_exp(float x) { return __expf(x); }
 template <typename T, bool CSMEM, int NT>
 __global__ void __launch_bounds__(NT) pk_dp_kernel(const DpArgs a) {
     constexpr int NW = NT / 32;
+#ifndef PK_UNROLL
+#define PK_UNROLL 4
+#endif
+    constexpr int U = PK_UNROLL;   // rows in flight per lane: child cells of U rows are gathered before the U Gaussians
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ long long s_work[2];
     __shared__ int s_coff[PK_MAX_CLASSES + 1];
     __shared__ int s_cntB[PK_MAX_CLASSES];
     __shared__ double s_part[32];
+    __shared__ double s_tab[PK_EXP_TAB];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned char *sA = smem;
     unsigned char *sB = smem + a.tree_region;
-    int4 *rowinfo = reinterpret_cast<int4 *>(smem + 2 * (size_t)a.tree_region);
+    RowRec<T> *rowrec = reinterpret_cast<RowRec<T> *>(smem + 2 * (size_t)a.tree_region);
     T *C = CSMEM ? reinterpret_cast<T *>(smem + 2 * (size_t)a.tree_region + a.rowinfo_bytes)
                  : reinterpret_cast<T *>(a.scratch) + (size_t)blockIdx.x * (size_t)a.slab_elems;
 
     if (tid == 0) mbar_init(&s_bar, 1);
+    if (tid < PK_EXP_TAB) s_tab[tid] = a.exp_tab[tid];
     __syncthreads();
     uint32_t parity = 0;
     const T lambda = (T)a.lambda, sigma = (T)a.sigma, neg_inv_tau = (T)a.neg_inv_tau;
@@ -172,9 +242,10 @@ __global__ void __launch_bounds__(NT) pk_dp_kernel(const DpArgs a) {
         const int *codeB0 = reinterpret_cast<const int *>(sB + hB[8]);
         const int *codeB1 = reinterpret_cast<const int *>(sB + hB[9]);
 
-        // ---- compact C layout: cell 0 holds lambda (the "tip x tip" value), then one rectangle per class
+        // ---- compact C layout (cells hold sigma + C, the factor a parent multiplies by): cell 0 = tip x tip,
+        //      cell 1 = 1 (no match), then one rectangle per class
         if (tid == 0) {
-            int off = 1;
+            int off = 2;
             for (int c = 0; c < ncls; ++c) {
                 const int wB = clsB[c + 1] - clsB[c];
                 s_cntB[c] = wB;
@@ -182,19 +253,21 @@ __global__ void __launch_bounds__(NT) pk_dp_kernel(const DpArgs a) {
                 off += (clsA[c + 1] - clsA[c]) * wB;
             }
             s_coff[ncls] = off;
-            C[0] = lambda;
+            C[0] = sigma + lambda;   // tip x tip child factor (phyloK2.py:194-196)
+            C[1] = (T)1;             // factor of a child slot whose productions differ (phyloK2.py:191-192)
         }
         __syncthreads();
-        // per row: {class+1 of child 0, C offset of child 0's row, same for child 1}
         for (int r = tid; r < nA; r += NT) {
             const int c0 = codeA0[r], c1 = codeA1[r];
             const int q0 = c0 >> 24, q1 = c1 >> 24;
-            int4 ri;
-            ri.x = q0;
-            ri.y = q0 ? s_coff[q0 - 1] + (c0 & 0xffffff) * s_cntB[q0 - 1] : 0;
-            ri.z = q1;
-            ri.w = q1 ? s_coff[q1 - 1] + (c1 & 0xffffff) * s_cntB[q1 - 1] : 0;
-            rowinfo[r] = ri;
+            RowRec<T> rec;
+            rec.a0 = a0p[r];
+            rec.a1 = a1p[r];
+            rec.q0 = q0;
+            rec.off0 = q0 ? s_coff[q0 - 1] + (c0 & 0xffffff) * s_cntB[q0 - 1] : 0;
+            rec.q1 = q1;
+            rec.off1 = q1 ? s_coff[q1 - 1] + (c1 & 0xffffff) * s_cntB[q1 - 1] : 0;
+            rowrec[r] = rec;
         }
         __syncthreads();
 
@@ -210,14 +283,13 @@ __global__ void __launch_bounds__(NT) pk_dp_kernel(const DpArgs a) {
                 // balanced split of the (column chunk, row) space of this rectangle over the warps: each warp gets a
                 // contiguous run of rows of one column chunk (spilling into the next chunk at most once or twice)
                 const int total = rows * nch;
-                const int per = (total + NW - 1) / NW;
+                const int per = (total + NW - 1) / NW;           // NW is a power of two
                 const int colbase = clsB[c], rowcls = clsA[c], coff = s_coff[c];
-                int wv = warp - (itembase % NW);
-                if (wv < 0) wv += NW;
+                const int wv = (warp - itembase) & (NW - 1);
                 int idx = wv * per;
                 const int end = min(total, idx + per);
                 if (idx < end) {
-                    int ch = idx / rows;
+                    int ch = pk_div(idx, rows);
                     int r = idx - ch * rows;
                     while (idx < end) {
                         const int rcount = min(rows - r, end - idx);
@@ -228,15 +300,54 @@ __global__ void __launch_bounds__(NT) pk_dp_kernel(const DpArgs a) {
                             const int cb0 = codeB0[col], cb1 = codeB1[col];
                             const int qb0 = cb0 >> 24, kb0 = cb0 & 0xffffff, qb1 = cb1 >> 24, kb1 = cb1 & 0xffffff;
                             const int rbeg = r0 + r, rend = rbeg + rcount;
-                            T *crow = C + coff + (size_t)(rbeg - rowcls) * wB + jb;
+                            int cidx = coff + (rbeg - rowcls) * wB + jb;      // this lane's cell in row rbeg
+                            const RowRec<T> *rp = rowrec + rbeg;
                             T part = (T)0;
-                            for (int rr = rbeg; rr < rend; ++rr, crow += wB) {
-                                const T d0 = a0p[rr] - b0, d1 = a1p[rr] - b1;
-                                const int4 ri = rowinfo[rr];
-                                T v = lambda * pk_exp((d0 * d0 + d1 * d1) * neg_inv_tau);
-                                if (ri.x == qb0) v *= sigma + C[ri.y + kb0];
-                                if (ri.z == qb1) v *= sigma + C[ri.w + kb1];
-                                *crow = v;
+                            int rr = rbeg;
+                            // software pipeline: the child-cell gathers of the NEXT group of U rows are issued
+                            // before the Gaussians of the current group, so their (L2/HBM) latency is covered
+                            T f0[U], f1[U];
+                            if (rr + U <= rend) {
+#pragma unroll
+                                for (int u = 0; u < U; ++u) {
+                                    const RowRec<T> rec = rp[u];
+                                    f0[u] = C[rec.q0 == qb0 ? rec.off0 + kb0 : 1];
+                                    f1[u] = C[rec.q1 == qb1 ? rec.off1 + kb1 : 1];
+                                }
+                            }
+                            for (; rr + U <= rend; rr += U, rp += U, cidx += U * wB) {
+                                T x[U], e[U], g[U];
+#pragma unroll
+                                for (int u = 0; u < U; ++u) {
+                                    const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
+                                    x[u] = (d0 * d0 + d1 * d1) * neg_inv_tau;
+                                    g[u] = f0[u] * f1[u];
+                                }
+                                if (rr + 2 * U <= rend) {
+#pragma unroll
+                                    for (int u = 0; u < U; ++u) {
+                                        const RowRec<T> rec = rp[U + u];
+                                        f0[u] = C[rec.q0 == qb0 ? rec.off0 + kb0 : 1];
+                                        f1[u] = C[rec.q1 == qb1 ? rec.off1 + kb1 : 1];
+                                    }
+                                }
+                                pk_gauss<U>(x, e, s_tab, lambda);
+#pragma unroll
+                                for (int u = 0; u < U; ++u) {
+                                    const T v = e[u] * g[u];
+                                    C[cidx + u * wB] = v + sigma;
+                                    part += v;
+                                }
+                            }
+                            for (; rr < rend; ++rr, ++rp, cidx += wB) {
+                                const RowRec<T> rec = *rp;
+                                const T g0 = C[rec.q0 == qb0 ? rec.off0 + kb0 : 1];
+                                const T g1 = C[rec.q1 == qb1 ? rec.off1 + kb1 : 1];
+                                const T d0 = rec.a0 - b0, d1 = rec.a1 - b1;
+                                T x1[1] = {(d0 * d0 + d1 * d1) * neg_inv_tau}, e1[1];
+                                pk_gauss<1>(x1, e1, s_tab, lambda);
+                                const T v = e1[0] * g0 * g1;
+                                C[cidx] = v + sigma;
                                 part += v;
                             }
                             acc += (double)part;
@@ -246,7 +357,7 @@ __global__ void __launch_bounds__(NT) pk_dp_kernel(const DpArgs a) {
                         ++ch;
                     }
                 }
-                itembase += (total + per - 1) / per;
+                itembase += pk_div(total + per - 1, per);
             }
             __syncthreads();
         }
@@ -634,35 +745,31 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
     args.lambda = p->decay;
     args.neg_inv_tau = -1.0 / p->gauss;
     args.sigma = p->sigma;
+    for (int j = 0; j < 64; ++j) args.exp_tab[j] = p->decay * std::exp2((double)j / 64.0);
 
     // upper bound of the compact C size over all pairs of the two forests
-    long long maxM = 1;
+    long long maxM = 2;   // cell 0 (tip x tip factor) and cell 1 (no-match factor) precede the class rectangles
     for (int c = 0; c < fa->ncls; ++c) maxM += (long long)fa->max_cnt[c] * fb->max_cnt[c];
     const int region = (std::max(fa->max_block, fb->max_block) + 127) & ~127;
-    const int rowinfo = ((std::max(fa->max_n, fb->max_n) * 16) + 127) & ~127;
+    const int rowinfo = ((std::max(fa->max_n, fb->max_n) * 32) + 127) & ~127;
     const long long base_smem = 2ll * region + rowinfo;
-    const long long limit = ctx->smem_optin - 1024;   // static shared memory of the kernel
+    const long long limit = ctx->smem_optin - 2048;   // static shared memory of the kernel
     if (base_smem > limit)
         return pk_fail(PK_ERR_INVALID, "trees too large to stage in shared memory (" + std::to_string(base_smem) +
                                            " bytes needed, " + std::to_string(limit) + " available)");
     const long long c_bytes = ((maxM * (long long)w) + 127) & ~127ll;
     bool csmem = !ctx->cfg_force_hbm && base_smem + c_bytes <= limit;
-    int nt = ctx->cfg_threads ? ctx->cfg_threads : (csmem ? 256 : 512);
     int smem = (int)(csmem ? base_smem + c_bytes : base_smem);
     args.tree_region = region;
     args.rowinfo_bytes = rowinfo;
 
-    int per_sm = 1;
+    // 256-thread CTAs: 8 warps share one pair (cheap level barriers), several pairs are resident per SM; measured
+    // best on B200 for both storage paths (profiles/r01_tuning.md)
+    int nt = ctx->cfg_threads ? ctx->cfg_threads : 256, per_sm = 0;
     cudaError_t e = PK_DISPATCH(occupancy_t, smem, &per_sm);
     if (e != cudaSuccess) return pk_fail(PK_ERR_CUDA, std::string("occupancy query: ") + cudaGetErrorString(e));
     if (per_sm < 1) return pk_fail(PK_ERR_CUDA, "kernel does not fit on an SM with the requested configuration");
     if (!csmem && ctx->cfg_ctas > 0) per_sm = std::min(per_sm, ctx->cfg_ctas);
-    if (!csmem && ctx->cfg_ctas == 0) {
-        // keep the C slabs of all resident CTAs inside L2 (~126 MB) when possible
-        long long slab_bytes = ((maxM * (long long)w) + 255) & ~255ll;
-        long long fit = (100ll << 20) / std::max(1ll, slab_bytes * ctx->sm_count);
-        per_sm = (int)std::max(1ll, std::min<long long>(per_sm, fit));
-    }
     long long grid_ll = std::min<long long>(args.total, (long long)per_sm * ctx->sm_count);
     int grid = (int)std::max(1ll, grid_ll);
     if (!csmem) {

@@ -1,0 +1,157 @@
+"""Gram-matrix driver over the GPUs of one box: the working, sharded form of ``PhyloKernel.compute_matrix``
+(``/root/reference/phyloK2.py:148-156``).
+
+Every (i, j) entry is an independent DP, so the upper triangle is cut into tile x tile blocks that are dealt
+round-robin to the ranks (one process per GPU, ``torch.distributed``).  Each rank holds the whole packed forest
+(tens of MB) and evaluates its blocks with no data-path collective.  The only thing that crosses NVLink is the
+result:
+
+* ``gather="p2p"`` (default for world > 1): rank 0 owns the N x N matrix; the other ranks map it through CUDA IPC and
+  their DP kernels store each K (and its mirror) straight into rank 0's HBM -- the result crosses NVLink exactly once,
+  written by the kernel that produced it, and there is no gather step at all (a barrier closes the step).
+* ``gather="allreduce"``: every rank fills its own zero-initialised matrix and one NCCL all-reduce (sum with zeros is
+  exact) leaves the full matrix on every rank.
+
+torch is used for the process group, streams and events only.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, pk_params
+from .phylokernel import Forest, get_context
+
+__all__ = ["GramRunner"]
+
+
+class GramRunner(object):
+    def __init__(self, flats, decayFactor=0.2, gaussFactor=2.0, sigma=1.0, precision=64, normalised=True, tile=32,
+                 gather="p2p", rank=0, world=1, device=None, group=None):
+        self.flats = list(flats)
+        self.n = len(self.flats)
+        self.params = pk_params(float(decayFactor), float(gaussFactor), float(sigma), int(precision), 0)
+        self.precision = int(precision)
+        self.normalised = bool(normalised)
+        self.tile = int(tile)
+        self.rank, self.world = int(rank), int(world)
+        self.gather = gather if self.world > 1 else "local"
+        self.group = group
+        self.ctx = get_context(device)
+        self.L = _lib.lib()
+        self.forest = None
+        self.d_out = ctypes.c_void_p()        # where this rank's kernel writes (local or rank 0's mapped buffer)
+        self.d_local = ctypes.c_void_p()      # buffer this rank owns (rank 0 always; all ranks for allreduce)
+        self.d_diag = ctypes.c_void_p()
+        self._torch_view = None
+        n = self.n
+        check(self.L.pk_device_alloc(self.ctx._h, 8 * n, ctypes.byref(self.d_diag)))
+        if self.gather in ("local", "allreduce") or self.rank == 0:
+            check(self.L.pk_device_alloc(self.ctx._h, 8 * n * n, ctypes.byref(self.d_local)))
+            check(self.L.pk_memset_d(self.ctx._h, self.d_local, 0, 8 * n * n))
+            self.d_out = self.d_local
+        if self.gather == "p2p":
+            self._share_rank0_buffer()
+
+    # -- setup ----------------------------------------------------------------------------------------
+    def _share_rank0_buffer(self):
+        import torch
+        import torch.distributed as dist
+        handle = torch.zeros(64, dtype=torch.uint8)
+        if self.rank == 0:
+            raw = (ctypes.c_ubyte * 64)()
+            check(self.L.pk_ipc_export(self.ctx._h, self.d_local, raw))
+            handle = torch.tensor(list(raw), dtype=torch.uint8)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        h = handle.to(dev)
+        dist.broadcast(h, src=0, group=self.group)
+        if self.rank != 0:
+            raw = (ctypes.c_ubyte * 64)(*h.cpu().tolist())
+            check(self.L.pk_ipc_open(self.ctx._h, raw, ctypes.byref(self.d_out)))
+
+    def upload(self):
+        """Host trees -> packed device forest (the H2D leg of the end-to-end path). Returns bytes copied."""
+        if self.forest is not None:
+            self.forest.close()
+        self.forest = Forest(self.ctx, self.flats, self.precision)
+        return self.forest.nbytes()
+
+    # -- one step ---------------------------------------------------------------------------------------
+    def launch(self):
+        """Asynchronously evaluate this rank's blocks (plus the N diagonal DPs every rank needs)."""
+        check(self.L.pk_forest_gram_part(self.ctx._h, self.forest._h, ctypes.byref(self.params),
+                                         1 if self.normalised else 0, self.tile, self.rank, self.world,
+                                         self.d_out, self.n, self.d_diag))
+
+    def finish(self):
+        """Close the step: after this, rank 0 (p2p) / every rank (allreduce) holds the full matrix in HBM."""
+        if self.world == 1:
+            return
+        import torch
+        import torch.distributed as dist
+        if self.gather == "allreduce":
+            if self._torch_view is None:
+                self._torch_view = _as_tensor(self.d_local.value, self.n * self.n)
+            dist.all_reduce(self._torch_view, group=self.group)
+        else:
+            self.ctx.sync()                      # peer stores issued by this rank's kernel are complete
+            dist.barrier(group=self.group)
+
+    def zero(self):
+        if self.d_local.value:
+            check(self.L.pk_memset_d(self.ctx._h, self.d_local, 0, 8 * self.n * self.n))
+
+    def fetch(self):
+        """Device -> host copy of the full matrix (rank 0 for p2p; any rank otherwise)."""
+        out = np.empty((self.n, self.n), np.float64)
+        check(self.L.pk_memcpy_d2h(self.ctx._h, out.ctypes.data, self.d_local, 8 * self.n * self.n))
+        return out
+
+    def my_stats(self):
+        st = self.forest.gram_stats(self.tile, self.rank, self.world)
+        st["node_sum"] = sum(self._node_sum_terms())
+        return st
+
+    def _node_sum_terms(self):
+        # sum over this rank's DPs of (n1 + n2): exact, from the tile assignment
+        n, t = self.n, self.tile
+        nint = np.array([f.n_internal for f in self.flats], dtype=np.int64)
+        nt = (n + t - 1) // t
+        k = 0
+        for ti in range(nt):
+            for tj in range(ti, nt):
+                if k % self.world == self.rank:
+                    a = nint[ti * t:min(n, (ti + 1) * t)]
+                    b = nint[tj * t:min(n, (tj + 1) * t)]
+                    if ti == tj:
+                        m = len(a)
+                        idx = np.triu_indices(m)
+                        yield int((a[idx[0]] + a[idx[1]]).sum())
+                    else:
+                        yield int(a.sum() * len(b) + b.sum() * len(a))
+                k += 1
+
+    def close(self):
+        if self.forest is not None:
+            self.forest.close()
+            self.forest = None
+        if self.gather == "p2p" and self.rank != 0 and self.d_out.value:
+            check(self.L.pk_ipc_close(self.ctx._h, self.d_out))
+            self.d_out = ctypes.c_void_p()
+        for buf in (self.d_local, self.d_diag):
+            if buf.value:
+                check(self.L.pk_device_free(self.ctx._h, buf))
+        self.d_local = ctypes.c_void_p()
+        self.d_diag = ctypes.c_void_p()
+
+
+def _as_tensor(ptr, numel):
+    """Zero-copy torch view (float64) of a device buffer owned by libphylok (for the NCCL all-reduce only)."""
+    import torch
+
+    class _Holder(object):
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(h, device=torch.device("cuda", torch.cuda.current_device()))

@@ -58,21 +58,30 @@ def kingman_newick(n, seed, states=0, prevalence=None):
     height = [0.0] * total
     blen = [0.0] * total
     names = _tip_names(n, rng, states, prevalence) + [None] * (n - 1)
+    waits = rng.exponential(size=n - 1)
+    picks = rng.random((n - 1, 2))
     active = list(range(n))
     t = 0.0
     nxt = n
-    while len(active) > 1:
+    for step in range(n - 1):
         k = len(active)
-        t += rng.exponential(2.0 / (k * (k - 1)))
-        i, j = rng.choice(k, size=2, replace=False)
+        t += waits[step] * (2.0 / (k * (k - 1)))
+        i = int(picks[step, 0] * k)
+        j = int(picks[step, 1] * (k - 1))
+        if j >= i:
+            j += 1
         a, b = active[i], active[j]
         children[nxt] = (a, b)
         height[nxt] = t
         blen[a] = t - height[a]
         blen[b] = t - height[b]
-        for idx in sorted((int(i), int(j)), reverse=True):
-            active.pop(idx)
-        active.append(nxt)
+        hi, lo = (i, j) if i > j else (j, i)
+        active[hi] = active[-1]
+        active.pop()
+        if lo < len(active):
+            active[lo] = nxt
+        else:                       # lo was the last slot and has just been popped (cannot happen: lo < hi)
+            active.append(nxt)
         nxt += 1
     return _emit(children, blen, names, active[0])
 
@@ -86,18 +95,24 @@ def yule_newick(n, seed, states=0, prevalence=None):
     blen = [0.0] * total
     root = 0
     leaves = [0]
+    waits = rng.exponential(size=n)
+    picks = rng.random(n)
     t = 0.0
     nxt = 1
+    step = 0
     while len(leaves) < n:
         k = len(leaves)
-        t += rng.exponential(1.0 / k)
-        v = leaves.pop(int(rng.integers(k)))
+        t += waits[step] / k
+        idx = int(picks[step] * k)
+        step += 1
+        v = leaves[idx]
         blen[v] = t - birth[v]
         children[v] = (nxt, nxt + 1)
         birth[nxt] = birth[nxt + 1] = t
-        leaves.extend((nxt, nxt + 1))
+        leaves[idx] = nxt
+        leaves.append(nxt + 1)
         nxt += 2
-    t += rng.exponential(1.0 / n)
+    t += waits[n - 1] / n
     for v in leaves:
         blen[v] = t - birth[v]
     tipnames = _tip_names(n, rng, states, prevalence)
