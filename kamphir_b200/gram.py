@@ -79,6 +79,8 @@ class GramRunner(object):
     # -- one step ---------------------------------------------------------------------------------------
     def launch(self):
         """Asynchronously evaluate this rank's blocks (plus the N diagonal DPs every rank needs)."""
+        if self.gather == "allreduce":
+            self.zero()                          # the all-reduce sums the ranks' disjoint blocks with zeros elsewhere
         check(self.L.pk_forest_gram_part(self.ctx._h, self.forest._h, ctypes.byref(self.params),
                                          1 if self.normalised else 0, self.tile, self.rank, self.world,
                                          self.d_out, self.n, self.d_diag))
