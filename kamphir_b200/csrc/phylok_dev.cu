@@ -96,13 +96,15 @@ __device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity) {
 // lambda * exp(x) for x <= 0, U independent values at a time
 // ---------------------------------------------------------------------------------------------------
 // fp64: x = (k/64) ln2 + r, |r| <= ln2/128; lambda*exp(x) = tab[k & 63] * 2^(k >> 6) * p(r) with tab[j] = lambda * 2^(j/64)
-// (64 doubles in shared memory, filled by the host in fp64) and p the degree-5 Taylor polynomial (remainder r^6/720
-// < 3.5e-17; measured max relative error 4e-16).  10 fp64-pipe instructions instead of the ~17 of the generic exp();
-// below x = -700 the result is ~2^-1022 (true value < 1e-304).  The U chains are written stage by stage so the
-// scheduler interleaves them (a single DFMA chain leaves the fp64 pipe idle most of the time).
+// (filled by the host in fp64) and p the degree-5 Taylor polynomial (remainder r^6/720 < 3.5e-17; measured max relative
+// error 4e-16).  10 fp64-pipe instructions instead of the ~17 of the generic exp(); below x = -700 the result is
+// ~2^-1022 (true value < 1e-304).  The table is replicated 16x in shared memory (entry j of lane l at word
+// (16 j + (l & 15))): a 64-bit LDS is served per half-warp, so every lookup is conflict-free (2 wavefronts instead of
+// ~4.5 measured with a single copy).  The U chains are written stage by stage so the scheduler interleaves them.
 #define PK_EXP_TAB 64
+#define PK_EXP_REP 16
 template <int U>
-__device__ __forceinline__ void pk_gauss(const double (&x)[U], double (&out)[U], const double *tab, double /*lambda*/) {
+__device__ __forceinline__ void pk_gauss(const double (&x)[U], double (&out)[U], const double *tab_lane, double /*lambda*/) {
     double t[U], r[U], q[U];
     int k[U];
 #pragma unroll
@@ -131,7 +133,7 @@ __device__ __forceinline__ void pk_gauss(const double (&x)[U], double (&out)[U],
         // x < -700 (hi word of x, as unsigned, beyond that of -700.0): pin k so the scale below stays a valid exponent
         const int kk = (unsigned)__double2hiint(x[u]) >= 0xC085E000u ? -1022 * 64 : k[u];
         const double p2 = __hiloint2double(__double2hiint(q[u]) + ((kk >> 6) << 20), __double2loint(q[u]));
-        out[u] = p2 * tab[kk & (PK_EXP_TAB - 1)];
+        out[u] = p2 * tab_lane[(kk & (PK_EXP_TAB - 1)) * PK_EXP_REP];
     }
 }
 template <int U>
@@ -158,23 +160,40 @@ struct __align__(16) RowRec<double> {
     int q0, off0, q1, off1;
 };
 
+// one (level, class) rectangle of the wavefront, precomputed per pair so the warps only read it
+struct __align__(16) LevelDesc {
+    int r0;         // first row (kernel order) of the rectangle
+    int rows;       // rows at this level in this class
+    int wB;         // columns = nodes of the column tree in this class
+    int colbase;    // first column (kernel order in the column tree)
+    int cbase;      // C index of (row r0, column 0)
+    int total;      // rows * column chunks
+    int per;        // (column chunk, row) items per warp
+    int flags;      // bits 0..7: first warp (rotation); bit 8: last rectangle of its level; bit 9: all-tip-children class
+};
+#define PK_DESC_MAX 192
+
 // ---------------------------------------------------------------------------------------------------
 // the DP kernel
 // ---------------------------------------------------------------------------------------------------
-template <typename T, bool CSMEM, int NT>
-__global__ void __launch_bounds__(NT) pk_dp_kernel(const DpArgs a) {
-    constexpr int NW = NT / 32;
 #ifndef PK_UNROLL
 #define PK_UNROLL 4
 #endif
-    constexpr int U = PK_UNROLL;   // rows in flight per lane: child cells of U rows are gathered before the U Gaussians
+template <typename T, bool CSMEM, int NT>
+#ifndef PK_MINB
+#define PK_MINB 1
+#endif
+__global__ void __launch_bounds__(NT, (NT <= 256 ? PK_MINB : 1)) pk_dp_kernel(const DpArgs a) {
+    constexpr int NW = NT / 32;
+    constexpr int U = PK_UNROLL;   // rows in flight per lane
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ long long s_work[2];
     __shared__ int s_coff[PK_MAX_CLASSES + 1];
     __shared__ int s_cntB[PK_MAX_CLASSES];
     __shared__ double s_part[32];
-    __shared__ double s_tab[PK_EXP_TAB];
+    __shared__ __align__(16) LevelDesc s_desc[PK_DESC_MAX];
+    __shared__ __align__(16) double s_tab[sizeof(T) == 8 ? PK_EXP_TAB * PK_EXP_REP : 2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned char *sA = smem;
@@ -184,10 +203,13 @@ __global__ void __launch_bounds__(NT) pk_dp_kernel(const DpArgs a) {
                  : reinterpret_cast<T *>(a.scratch) + (size_t)blockIdx.x * (size_t)a.slab_elems;
 
     if (tid == 0) mbar_init(&s_bar, 1);
-    if (tid < PK_EXP_TAB) s_tab[tid] = a.exp_tab[tid];
+    if (sizeof(T) == 8)
+        for (int i = tid; i < PK_EXP_TAB * PK_EXP_REP; i += NT) s_tab[i] = a.exp_tab[i / PK_EXP_REP];
     __syncthreads();
     uint32_t parity = 0;
     const T lambda = (T)a.lambda, sigma = (T)a.sigma, neg_inv_tau = (T)a.neg_inv_tau;
+    const T tip2 = (sigma + lambda) * (sigma + lambda);        // both children are tip x tip (phyloK2.py:194-196, twice)
+    const double *tab_lane = s_tab + (lane & (PK_EXP_REP - 1));
 
     for (unsigned it_no = 0;; ++it_no) {
         if (tid == 0) s_work[it_no & 1] = (long long)atomicAdd(a.counter, 1ull);
@@ -230,6 +252,7 @@ __global__ void __launch_bounds__(NT) pk_dp_kernel(const DpArgs a) {
         const int *hA = reinterpret_cast<const int *>(sA);
         const int *hB = reinterpret_cast<const int *>(sB);
         const int nA = hA[0], ncls = hA[1], nlevA = hA[2];
+        const unsigned long long tipmask = (unsigned)hA[12] | ((unsigned long long)(unsigned)hA[13] << 32);
         const int *clsA = reinterpret_cast<const int *>(sA + hA[4]);
         const int *lvlA = reinterpret_cast<const int *>(sA + hA[5]);
         const T *a0p = reinterpret_cast<const T *>(sA + hA[6]);
@@ -269,86 +292,135 @@ __global__ void __launch_bounds__(NT) pk_dp_kernel(const DpArgs a) {
             rec.off1 = q1 ? s_coff[q1 - 1] + (c1 & 0xffffff) * s_cntB[q1 - 1] : 0;
             rowrec[r] = rec;
         }
-        __syncthreads();
 
-        // ---- wavefront over the row tree's levels ------------------------------------------------
+        // ---- wavefront over the row tree's levels, a batch of levels at a time -------------------------
         double acc = 0.0;
-        for (int L = 0; L < nlevA; ++L) {
-            int itembase = 0;
-            for (int c = 0; c < ncls; ++c) {
-                const int r0 = lvlA[c * (nlevA + 1) + L], r1 = lvlA[c * (nlevA + 1) + L + 1];
-                const int rows = r1 - r0, wB = s_cntB[c];
-                if (rows <= 0 || wB <= 0) continue;
-                const int nch = (wB + 31) >> 5;
-                // balanced split of the (column chunk, row) space of this rectangle over the warps: each warp gets a
-                // contiguous run of rows of one column chunk (spilling into the next chunk at most once or twice)
-                const int total = rows * nch;
-                const int per = (total + NW - 1) / NW;           // NW is a power of two
-                const int colbase = clsB[c], rowcls = clsA[c], coff = s_coff[c];
-                const int wv = (warp - itembase) & (NW - 1);
-                int idx = wv * per;
-                const int end = min(total, idx + per);
+        const int lev_per_batch = max(1, PK_DESC_MAX / ncls);
+        for (int L0 = 0; L0 < nlevA; L0 += lev_per_batch) {
+            const int L1 = min(nlevA, L0 + lev_per_batch);
+            __syncthreads();                       // previous batch done with s_desc; rowrec / s_coff visible
+            // one thread per level writes that level's rectangles into its own slice (compacted by the reader below)
+            for (int L = L0 + tid; L < L1; L += NT) {
+                LevelDesc *dst = s_desc + (L - L0) * ncls;
+                int used = 0, n_out = 0;
+                for (int c = 0; c < ncls; ++c) {
+                    const int r0 = lvlA[c * (nlevA + 1) + L], rows = lvlA[c * (nlevA + 1) + L + 1] - r0, wB = s_cntB[c];
+                    LevelDesc d;
+                    d.r0 = r0; d.rows = 0; d.wB = wB; d.colbase = clsB[c]; d.cbase = 0; d.total = 0; d.per = 1; d.flags = 0;
+                    if (rows > 0 && wB > 0) {
+                        const int nch = (wB + 31) >> 5;
+                        d.rows = rows;
+                        d.cbase = s_coff[c] + (r0 - clsA[c]) * wB;
+                        d.total = rows * nch;
+                        d.per = (d.total + NW - 1) / NW;
+                        d.flags = (used & (NW - 1)) | (((tipmask >> c) & 1ull) ? 512 : 0);
+                        used += (d.total + d.per - 1) / d.per;
+                        ++n_out;
+                    }
+                    dst[c] = d;
+                }
+                // mark the last non-empty rectangle of the level (the level barrier follows it)
+                for (int c = ncls - 1; c >= 0; --c)
+                    if (dst[c].rows > 0) { dst[c].flags |= 256; break; }
+                (void)n_out;
+            }
+            __syncthreads();
+            const int ndesc = (L1 - L0) * ncls;
+            for (int e = 0; e < ndesc; ++e) {
+                const LevelDesc d = s_desc[e];
+                if (d.rows <= 0) continue;             // uniform
+                const int wv = (warp - (d.flags & 255)) & (NW - 1);
+                int idx = wv * d.per;
+                const int end = min(d.total, idx + d.per);
                 if (idx < end) {
+                    const int rows = d.rows, wB = d.wB;
                     int ch = pk_div(idx, rows);
                     int r = idx - ch * rows;
                     while (idx < end) {
                         const int rcount = min(rows - r, end - idx);
                         const int jb = (ch << 5) + lane;
                         if (jb < wB) {
-                            const int col = colbase + jb;
+                            const int col = d.colbase + jb;
                             const T b0 = b0p[col], b1 = b1p[col];
-                            const int cb0 = codeB0[col], cb1 = codeB1[col];
-                            const int qb0 = cb0 >> 24, kb0 = cb0 & 0xffffff, qb1 = cb1 >> 24, kb1 = cb1 & 0xffffff;
-                            const int rbeg = r0 + r, rend = rbeg + rcount;
-                            int cidx = coff + (rbeg - rowcls) * wB + jb;      // this lane's cell in row rbeg
+                            const int rbeg = d.r0 + r, rend = rbeg + rcount;
+                            int cidx = d.cbase + r * wB + jb;        // this lane's cell in row rbeg
                             const RowRec<T> *rp = rowrec + rbeg;
                             T part = (T)0;
                             int rr = rbeg;
-                            // software pipeline: the child-cell gathers of the NEXT group of U rows are issued
-                            // before the Gaussians of the current group, so their (L2/HBM) latency is covered
-                            T f0[U], f1[U];
-                            if (rr + U <= rend) {
-#pragma unroll
-                                for (int u = 0; u < U; ++u) {
-                                    const RowRec<T> rec = rp[u];
-                                    f0[u] = C[rec.q0 == qb0 ? rec.off0 + kb0 : 1];
-                                    f1[u] = C[rec.q1 == qb1 ? rec.off1 + kb1 : 1];
-                                }
-                            }
-                            for (; rr + U <= rend; rr += U, rp += U, cidx += U * wB) {
-                                T x[U], e[U], g[U];
-#pragma unroll
-                                for (int u = 0; u < U; ++u) {
-                                    const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
-                                    x[u] = (d0 * d0 + d1 * d1) * neg_inv_tau;
-                                    g[u] = f0[u] * f1[u];
-                                }
-                                if (rr + 2 * U <= rend) {
+                            if (d.flags & 512) {
+                                // class whose nodes have two tip children: no child cells, f0*f1 = (sigma+lambda)^2
+                                for (; rr + U <= rend; rr += U, rp += U, cidx += U * wB) {
+                                    T x[U], ev[U];
 #pragma unroll
                                     for (int u = 0; u < U; ++u) {
-                                        const RowRec<T> rec = rp[U + u];
+                                        const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
+                                        x[u] = (d0 * d0 + d1 * d1) * neg_inv_tau;
+                                    }
+                                    pk_gauss<U>(x, ev, tab_lane, lambda);
+#pragma unroll
+                                    for (int u = 0; u < U; ++u) {
+                                        const T v = ev[u] * tip2;
+                                        C[cidx + u * wB] = v + sigma;
+                                        part += v;
+                                    }
+                                }
+                                for (; rr < rend; ++rr, ++rp, cidx += wB) {
+                                    const T d0 = rp->a0 - b0, d1 = rp->a1 - b1;
+                                    T x1[1] = {(d0 * d0 + d1 * d1) * neg_inv_tau}, e1[1];
+                                    pk_gauss<1>(x1, e1, tab_lane, lambda);
+                                    const T v = e1[0] * tip2;
+                                    C[cidx] = v + sigma;
+                                    part += v;
+                                }
+                            } else {
+                                const int cb0 = codeB0[col], cb1 = codeB1[col];
+                                const int qb0 = cb0 >> 24, kb0 = cb0 & 0xffffff, qb1 = cb1 >> 24, kb1 = cb1 & 0xffffff;
+                                // software pipeline: the child-cell gathers of the NEXT group of U rows are issued
+                                // before the Gaussians of the current group, so their (L2/HBM) latency is covered
+                                T f0[U], f1[U];
+                                if (rr + U <= rend) {
+#pragma unroll
+                                    for (int u = 0; u < U; ++u) {
+                                        const RowRec<T> rec = rp[u];
                                         f0[u] = C[rec.q0 == qb0 ? rec.off0 + kb0 : 1];
                                         f1[u] = C[rec.q1 == qb1 ? rec.off1 + kb1 : 1];
                                     }
                                 }
-                                pk_gauss<U>(x, e, s_tab, lambda);
+                                for (; rr + U <= rend; rr += U, rp += U, cidx += U * wB) {
+                                    T x[U], ev[U], g[U];
 #pragma unroll
-                                for (int u = 0; u < U; ++u) {
-                                    const T v = e[u] * g[u];
-                                    C[cidx + u * wB] = v + sigma;
+                                    for (int u = 0; u < U; ++u) {
+                                        const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
+                                        x[u] = (d0 * d0 + d1 * d1) * neg_inv_tau;
+                                        g[u] = f0[u] * f1[u];
+                                    }
+                                    if (rr + 2 * U <= rend) {
+#pragma unroll
+                                        for (int u = 0; u < U; ++u) {
+                                            const RowRec<T> rec = rp[U + u];
+                                            f0[u] = C[rec.q0 == qb0 ? rec.off0 + kb0 : 1];
+                                            f1[u] = C[rec.q1 == qb1 ? rec.off1 + kb1 : 1];
+                                        }
+                                    }
+                                    pk_gauss<U>(x, ev, tab_lane, lambda);
+#pragma unroll
+                                    for (int u = 0; u < U; ++u) {
+                                        const T v = ev[u] * g[u];
+                                        C[cidx + u * wB] = v + sigma;
+                                        part += v;
+                                    }
+                                }
+                                for (; rr < rend; ++rr, ++rp, cidx += wB) {
+                                    const RowRec<T> rec = *rp;
+                                    const T g0 = C[rec.q0 == qb0 ? rec.off0 + kb0 : 1];
+                                    const T g1 = C[rec.q1 == qb1 ? rec.off1 + kb1 : 1];
+                                    const T d0 = rec.a0 - b0, d1 = rec.a1 - b1;
+                                    T x1[1] = {(d0 * d0 + d1 * d1) * neg_inv_tau}, e1[1];
+                                    pk_gauss<1>(x1, e1, tab_lane, lambda);
+                                    const T v = e1[0] * g0 * g1;
+                                    C[cidx] = v + sigma;
                                     part += v;
                                 }
-                            }
-                            for (; rr < rend; ++rr, ++rp, cidx += wB) {
-                                const RowRec<T> rec = *rp;
-                                const T g0 = C[rec.q0 == qb0 ? rec.off0 + kb0 : 1];
-                                const T g1 = C[rec.q1 == qb1 ? rec.off1 + kb1 : 1];
-                                const T d0 = rec.a0 - b0, d1 = rec.a1 - b1;
-                                T x1[1] = {(d0 * d0 + d1 * d1) * neg_inv_tau}, e1[1];
-                                pk_gauss<1>(x1, e1, s_tab, lambda);
-                                const T v = e1[0] * g0 * g1;
-                                C[cidx] = v + sigma;
-                                part += v;
                             }
                             acc += (double)part;
                         }
@@ -357,9 +429,8 @@ __global__ void __launch_bounds__(NT) pk_dp_kernel(const DpArgs a) {
                         ++ch;
                     }
                 }
-                itembase += pk_div(total + per - 1, per);
+                if (d.flags & 256) __syncthreads();      // end of a level: its cells are final before the next one reads
             }
-            __syncthreads();
         }
 
         // ---- deterministic block reduction of K ---------------------------------------------------
@@ -753,7 +824,7 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
     const int region = (std::max(fa->max_block, fb->max_block) + 127) & ~127;
     const int rowinfo = ((std::max(fa->max_n, fb->max_n) * 32) + 127) & ~127;
     const long long base_smem = 2ll * region + rowinfo;
-    const long long limit = ctx->smem_optin - 2048;   // static shared memory of the kernel
+    const long long limit = ctx->smem_optin - 16384;   // static shared memory (table, level descriptors, ...)   // static shared memory of the kernel
     if (base_smem > limit)
         return pk_fail(PK_ERR_INVALID, "trees too large to stage in shared memory (" + std::to_string(base_smem) +
                                            " bytes needed, " + std::to_string(limit) + " available)");

@@ -454,6 +454,19 @@ void pk_block_pack(const pk_tree &t, int precision, unsigned char *dst) {
     int32_t *hdr = reinterpret_cast<int32_t *>(dst);
     size_t off = PK_HDR_INTS * 4;
     hdr[0] = t.n; hdr[1] = t.ncls; hdr[2] = t.nlev; hdr[3] = (int32_t)total; hdr[10] = t.ntips; hdr[11] = precision;
+    {   // classes whose nodes all have two tip children (their cells need no child-cell gathers); bit c of hdr[12..13]
+        uint64_t mask = 0;
+        for (int c = 0; c < t.ncls; ++c) {
+            bool all = true;
+            for (int32_t row = t.cls_start[c]; row < t.cls_start[c + 1] && all; ++row) {
+                const int32_t i = t.order[row];
+                all = t.cidx[2 * (size_t)i] < 0 && t.cidx[2 * (size_t)i + 1] < 0;
+            }
+            if (all) mask |= (uint64_t)1 << c;
+        }
+        hdr[12] = (int32_t)(mask & 0xffffffffu);
+        hdr[13] = (int32_t)(mask >> 32);
+    }
     hdr[4] = (int32_t)off;
     std::memcpy(dst + off, t.cls_start.data(), (size_t)(t.ncls + 1) * 4);
     off += align16((size_t)(t.ncls + 1) * 4);

@@ -38,7 +38,8 @@ struct pk_tree {
 
 // Device block of one tree (16-byte aligned, staged into shared memory with one bulk copy):
 //   int32 hdr[16]   : 0 n | 1 ncls | 2 nlev | 3 block bytes | 4 off cls_start | 5 off lvl | 6 off bl0 | 7 off bl1 |
-//                     8 off code0 | 9 off code1 | 10 ntips | 11 precision            (offsets in bytes from block start)
+//                     8 off code0 | 9 off code1 | 10 ntips | 11 precision | 12,13 bitmask of all-tip-children classes
+//                     (offsets in bytes from block start)
 //   int32 cls_start[ncls + 1]
 //   int32 lvl[ncls][nlev + 1]
 //   real  bl0[n], bl1[n]          (real = double or float; kernel order)
