@@ -105,7 +105,8 @@ int pk_ctx_create(int device, pk_ctx **out);
 void pk_ctx_destroy(pk_ctx *ctx);
 int pk_ctx_set_stream(pk_ctx *ctx, void *cuda_stream);   /* run on a caller-owned cudaStream_t (NULL = own stream) */
 int pk_ctx_sync(pk_ctx *ctx);
-/* tuning knobs (0 = default): threads per CTA, CTAs per SM for the HBM-resident path */
+/* tuning knobs (0 = default): threads per CTA (multiple of 32, >= widest class), CTAs per SM for the HBM-slab path,
+ * C storage: 0 = automatic (shared memory only when it costs no resident CTAs), 1 = HBM slabs, 2 = shared memory */
 int pk_ctx_configure(pk_ctx *ctx, int32_t threads, int32_t ctas_per_sm, int32_t force_hbm);
 /* the most recent DP kernel launch on this ctx: ms = its device time (CUDA events recorded around that launch on the
  * ctx stream; blocks until it finished), launches = DP kernels launched since ctx creation, path = 0 (C in shared

@@ -163,13 +163,12 @@ struct __align__(16) RowRec<double> {
 // one (level, class) rectangle of the wavefront, precomputed per pair so the warps only read it
 struct __align__(16) LevelDesc {
     int r0;         // first row (kernel order) of the rectangle
-    int rows;       // rows at this level in this class
+    int rows;       // rows at this level in this class (0: empty, skipped)
     int wB;         // columns = nodes of the column tree in this class
     int colbase;    // first column (kernel order in the column tree)
     int cbase;      // C index of (row r0, column 0)
-    int total;      // rows * column chunks
-    int per;        // (column chunk, row) items per warp
-    int flags;      // bits 0..7: first warp (rotation); bit 8: last rectangle of its level; bit 9: all-tip-children class
+    int flags;      // bit 8: last rectangle of its level (a barrier follows); bit 9: all-tip-children class
+    int pad0, pad1;
 };
 #define PK_DESC_MAX 192
 
@@ -179,12 +178,16 @@ struct __align__(16) LevelDesc {
 #ifndef PK_UNROLL
 #define PK_UNROLL 4
 #endif
-template <typename T, bool CSMEM, int NT>
 #ifndef PK_MINB
-#define PK_MINB 1
+#define PK_MINB 3
 #endif
-__global__ void __launch_bounds__(NT, (NT <= 256 ? PK_MINB : 1)) pk_dp_kernel(const DpArgs a) {
-    constexpr int NW = NT / 32;
+// Column-stationary mapping: warp w owns columns [32w, 32w+32) of every class rectangle, a lane one column.  Every warp
+// therefore walks the same rows of a (level, class) rectangle -- no work splitting, no per-warp bookkeeping, perfectly
+// balanced level barriers -- and a CTA has as many warps as the widest class needs (6 for 500-tip trees), several CTAs
+// (pairs) being resident per SM.
+template <typename T, bool CSMEM, int BOUND>     // BOUND: upper bound of the CTA size (sets the register budget)
+__global__ void __launch_bounds__(BOUND, (BOUND <= 256 ? PK_MINB : 1)) pk_dp_kernel(const DpArgs a) {
+    const int NT = blockDim.x, NW = NT >> 5;       // any multiple of 32 up to BOUND
     constexpr int U = PK_UNROLL;   // rows in flight per lane
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long s_bar;
@@ -210,6 +213,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? PK_MINB : 1)) pk_dp_kernel(co
     const T lambda = (T)a.lambda, sigma = (T)a.sigma, neg_inv_tau = (T)a.neg_inv_tau;
     const T tip2 = (sigma + lambda) * (sigma + lambda);        // both children are tip x tip (phyloK2.py:194-196, twice)
     const double *tab_lane = s_tab + (lane & (PK_EXP_REP - 1));
+    const int jb = tid;                                        // this thread's column within every class rectangle
 
     for (unsigned it_no = 0;; ++it_no) {
         if (tid == 0) s_work[it_no & 1] = (long long)atomicAdd(a.counter, 1ull);
@@ -299,135 +303,113 @@ __global__ void __launch_bounds__(NT, (NT <= 256 ? PK_MINB : 1)) pk_dp_kernel(co
         for (int L0 = 0; L0 < nlevA; L0 += lev_per_batch) {
             const int L1 = min(nlevA, L0 + lev_per_batch);
             __syncthreads();                       // previous batch done with s_desc; rowrec / s_coff visible
-            // one thread per level writes that level's rectangles into its own slice (compacted by the reader below)
-            for (int L = L0 + tid; L < L1; L += NT) {
+            for (int L = L0 + tid; L < L1; L += NT) {          // one thread per level describes its rectangles
                 LevelDesc *dst = s_desc + (L - L0) * ncls;
-                int used = 0, n_out = 0;
+                int last = -1;
                 for (int c = 0; c < ncls; ++c) {
                     const int r0 = lvlA[c * (nlevA + 1) + L], rows = lvlA[c * (nlevA + 1) + L + 1] - r0, wB = s_cntB[c];
                     LevelDesc d;
-                    d.r0 = r0; d.rows = 0; d.wB = wB; d.colbase = clsB[c]; d.cbase = 0; d.total = 0; d.per = 1; d.flags = 0;
+                    d.r0 = r0; d.rows = 0; d.wB = wB; d.colbase = clsB[c]; d.cbase = 0; d.flags = 0; d.pad0 = d.pad1 = 0;
                     if (rows > 0 && wB > 0) {
-                        const int nch = (wB + 31) >> 5;
                         d.rows = rows;
                         d.cbase = s_coff[c] + (r0 - clsA[c]) * wB;
-                        d.total = rows * nch;
-                        d.per = (d.total + NW - 1) / NW;
-                        d.flags = (used & (NW - 1)) | (((tipmask >> c) & 1ull) ? 512 : 0);
-                        used += (d.total + d.per - 1) / d.per;
-                        ++n_out;
+                        d.flags = ((tipmask >> c) & 1ull) ? 512 : 0;
+                        last = c;
                     }
                     dst[c] = d;
                 }
-                // mark the last non-empty rectangle of the level (the level barrier follows it)
-                for (int c = ncls - 1; c >= 0; --c)
-                    if (dst[c].rows > 0) { dst[c].flags |= 256; break; }
-                (void)n_out;
+                if (last >= 0) dst[last].flags |= 256;
             }
             __syncthreads();
             const int ndesc = (L1 - L0) * ncls;
             for (int e = 0; e < ndesc; ++e) {
                 const LevelDesc d = s_desc[e];
                 if (d.rows <= 0) continue;             // uniform
-                const int wv = (warp - (d.flags & 255)) & (NW - 1);
-                int idx = wv * d.per;
-                const int end = min(d.total, idx + d.per);
-                if (idx < end) {
-                    const int rows = d.rows, wB = d.wB;
-                    int ch = pk_div(idx, rows);
-                    int r = idx - ch * rows;
-                    while (idx < end) {
-                        const int rcount = min(rows - r, end - idx);
-                        const int jb = (ch << 5) + lane;
-                        if (jb < wB) {
-                            const int col = d.colbase + jb;
-                            const T b0 = b0p[col], b1 = b1p[col];
-                            const int rbeg = d.r0 + r, rend = rbeg + rcount;
-                            int cidx = d.cbase + r * wB + jb;        // this lane's cell in row rbeg
-                            const RowRec<T> *rp = rowrec + rbeg;
-                            T part = (T)0;
-                            int rr = rbeg;
-                            if (d.flags & 512) {
-                                // class whose nodes have two tip children: no child cells, f0*f1 = (sigma+lambda)^2
-                                for (; rr + U <= rend; rr += U, rp += U, cidx += U * wB) {
-                                    T x[U], ev[U];
+                const int wB = d.wB;
+                if (jb < wB) {
+                    const int col = d.colbase + jb;
+                    const T b0 = b0p[col], b1 = b1p[col];
+                    const int rend = d.r0 + d.rows;
+                    int cidx = d.cbase + jb;                     // this thread's cell in row r0
+                    const RowRec<T> *rp = rowrec + d.r0;
+                    T part = (T)0;
+                    int rr = d.r0;
+                    if (d.flags & 512) {
+                        // class whose nodes have two tip children: no child cells, f0*f1 = (sigma+lambda)^2
+                        for (; rr + U <= rend; rr += U, rp += U, cidx += U * wB) {
+                            T x[U], ev[U];
 #pragma unroll
-                                    for (int u = 0; u < U; ++u) {
-                                        const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
-                                        x[u] = (d0 * d0 + d1 * d1) * neg_inv_tau;
-                                    }
-                                    pk_gauss<U>(x, ev, tab_lane, lambda);
+                            for (int u = 0; u < U; ++u) {
+                                const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
+                                x[u] = (d0 * d0 + d1 * d1) * neg_inv_tau;
+                            }
+                            pk_gauss<U>(x, ev, tab_lane, lambda);
 #pragma unroll
-                                    for (int u = 0; u < U; ++u) {
-                                        const T v = ev[u] * tip2;
-                                        C[cidx + u * wB] = v + sigma;
-                                        part += v;
-                                    }
-                                }
-                                for (; rr < rend; ++rr, ++rp, cidx += wB) {
-                                    const T d0 = rp->a0 - b0, d1 = rp->a1 - b1;
-                                    T x1[1] = {(d0 * d0 + d1 * d1) * neg_inv_tau}, e1[1];
-                                    pk_gauss<1>(x1, e1, tab_lane, lambda);
-                                    const T v = e1[0] * tip2;
-                                    C[cidx] = v + sigma;
-                                    part += v;
-                                }
-                            } else {
-                                const int cb0 = codeB0[col], cb1 = codeB1[col];
-                                const int qb0 = cb0 >> 24, kb0 = cb0 & 0xffffff, qb1 = cb1 >> 24, kb1 = cb1 & 0xffffff;
-                                // software pipeline: the child-cell gathers of the NEXT group of U rows are issued
-                                // before the Gaussians of the current group, so their (L2/HBM) latency is covered
-                                T f0[U], f1[U];
-                                if (rr + U <= rend) {
+                            for (int u = 0; u < U; ++u) {
+                                const T v = ev[u] * tip2;
+                                C[cidx + u * wB] = v + sigma;
+                                part += v;
+                            }
+                        }
+                        for (; rr < rend; ++rr, ++rp, cidx += wB) {
+                            const T d0 = rp->a0 - b0, d1 = rp->a1 - b1;
+                            T x1[1] = {(d0 * d0 + d1 * d1) * neg_inv_tau}, e1[1];
+                            pk_gauss<1>(x1, e1, tab_lane, lambda);
+                            const T v = e1[0] * tip2;
+                            C[cidx] = v + sigma;
+                            part += v;
+                        }
+                    } else {
+                        const int cb0 = codeB0[col], cb1 = codeB1[col];
+                        const int qb0 = cb0 >> 24, kb0 = cb0 & 0xffffff, qb1 = cb1 >> 24, kb1 = cb1 & 0xffffff;
+                        // software pipeline: the child-cell gathers of the NEXT group of U rows are issued before the
+                        // Gaussians of the current group, so their (L2/HBM) latency is covered
+                        T f0[U], f1[U];
+                        if (rr + U <= rend) {
 #pragma unroll
-                                    for (int u = 0; u < U; ++u) {
-                                        const RowRec<T> rec = rp[u];
-                                        f0[u] = C[rec.q0 == qb0 ? rec.off0 + kb0 : 1];
-                                        f1[u] = C[rec.q1 == qb1 ? rec.off1 + kb1 : 1];
-                                    }
-                                }
-                                for (; rr + U <= rend; rr += U, rp += U, cidx += U * wB) {
-                                    T x[U], ev[U], g[U];
+                            for (int u = 0; u < U; ++u) {
+                                const RowRec<T> rec = rp[u];
+                                f0[u] = C[rec.q0 == qb0 ? rec.off0 + kb0 : 1];
+                                f1[u] = C[rec.q1 == qb1 ? rec.off1 + kb1 : 1];
+                            }
+                        }
+                        for (; rr + U <= rend; rr += U, rp += U, cidx += U * wB) {
+                            T x[U], ev[U], g[U];
 #pragma unroll
-                                    for (int u = 0; u < U; ++u) {
-                                        const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
-                                        x[u] = (d0 * d0 + d1 * d1) * neg_inv_tau;
-                                        g[u] = f0[u] * f1[u];
-                                    }
-                                    if (rr + 2 * U <= rend) {
+                            for (int u = 0; u < U; ++u) {
+                                const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
+                                x[u] = (d0 * d0 + d1 * d1) * neg_inv_tau;
+                                g[u] = f0[u] * f1[u];
+                            }
+                            if (rr + 2 * U <= rend) {
 #pragma unroll
-                                        for (int u = 0; u < U; ++u) {
-                                            const RowRec<T> rec = rp[U + u];
-                                            f0[u] = C[rec.q0 == qb0 ? rec.off0 + kb0 : 1];
-                                            f1[u] = C[rec.q1 == qb1 ? rec.off1 + kb1 : 1];
-                                        }
-                                    }
-                                    pk_gauss<U>(x, ev, tab_lane, lambda);
-#pragma unroll
-                                    for (int u = 0; u < U; ++u) {
-                                        const T v = ev[u] * g[u];
-                                        C[cidx + u * wB] = v + sigma;
-                                        part += v;
-                                    }
-                                }
-                                for (; rr < rend; ++rr, ++rp, cidx += wB) {
-                                    const RowRec<T> rec = *rp;
-                                    const T g0 = C[rec.q0 == qb0 ? rec.off0 + kb0 : 1];
-                                    const T g1 = C[rec.q1 == qb1 ? rec.off1 + kb1 : 1];
-                                    const T d0 = rec.a0 - b0, d1 = rec.a1 - b1;
-                                    T x1[1] = {(d0 * d0 + d1 * d1) * neg_inv_tau}, e1[1];
-                                    pk_gauss<1>(x1, e1, tab_lane, lambda);
-                                    const T v = e1[0] * g0 * g1;
-                                    C[cidx] = v + sigma;
-                                    part += v;
+                                for (int u = 0; u < U; ++u) {
+                                    const RowRec<T> rec = rp[U + u];
+                                    f0[u] = C[rec.q0 == qb0 ? rec.off0 + kb0 : 1];
+                                    f1[u] = C[rec.q1 == qb1 ? rec.off1 + kb1 : 1];
                                 }
                             }
-                            acc += (double)part;
+                            pk_gauss<U>(x, ev, tab_lane, lambda);
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                const T v = ev[u] * g[u];
+                                C[cidx + u * wB] = v + sigma;
+                                part += v;
+                            }
                         }
-                        idx += rcount;
-                        r = 0;
-                        ++ch;
+                        for (; rr < rend; ++rr, ++rp, cidx += wB) {
+                            const RowRec<T> rec = *rp;
+                            const T g0 = C[rec.q0 == qb0 ? rec.off0 + kb0 : 1];
+                            const T g1 = C[rec.q1 == qb1 ? rec.off1 + kb1 : 1];
+                            const T d0 = rec.a0 - b0, d1 = rec.a1 - b1;
+                            T x1[1] = {(d0 * d0 + d1 * d1) * neg_inv_tau}, e1[1];
+                            pk_gauss<1>(x1, e1, tab_lane, lambda);
+                            const T v = e1[0] * g0 * g1;
+                            C[cidx] = v + sigma;
+                            part += v;
+                        }
                     }
+                    acc += (double)part;
                 }
                 if (d.flags & 256) __syncthreads();      // end of a level: its cells are final before the next one reads
             }
@@ -585,8 +567,8 @@ extern "C" int pk_ctx_sync(pk_ctx *ctx) {
 
 extern "C" int pk_ctx_configure(pk_ctx *ctx, int32_t threads, int32_t ctas_per_sm, int32_t force_hbm) {
     if (!ctx) return pk_fail(PK_ERR_INVALID, "null ctx");
-    if (threads != 0 && threads != 128 && threads != 256 && threads != 512 && threads != 1024)
-        return pk_fail(PK_ERR_INVALID, "threads must be 0, 128, 256, 512 or 1024");
+    if (threads < 0 || threads > 1024 || (threads & 31))
+        return pk_fail(PK_ERR_INVALID, "threads must be 0 or a multiple of 32 up to 1024");
     ctx->cfg_threads = threads;
     ctx->cfg_ctas = ctas_per_sm;
     ctx->cfg_force_hbm = force_hbm;
@@ -764,38 +746,26 @@ extern "C" int pk_forest_pair_stats(const pk_forest *fa, const pk_forest *fb, co
 // ---------------------------------------------------------------------------------------------------
 // launch
 // ---------------------------------------------------------------------------------------------------
-template <typename T, bool CSMEM, int NT>
-static cudaError_t launch_t(const DpArgs &args, int grid, int smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(pk_dp_kernel<T, CSMEM, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+template <typename T, bool CSMEM, int BOUND>
+static cudaError_t launch_t(const DpArgs &args, int grid, int nt, int smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(pk_dp_kernel<T, CSMEM, BOUND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    pk_dp_kernel<T, CSMEM, NT><<<grid, NT, smem, stream>>>(args);
+    pk_dp_kernel<T, CSMEM, BOUND><<<grid, nt, smem, stream>>>(args);
     return cudaGetLastError();
 }
 
-template <typename T, bool CSMEM, int NT>
-static cudaError_t occupancy_t(int smem, int *blocks) {
-    cudaError_t e = cudaFuncSetAttribute(pk_dp_kernel<T, CSMEM, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+template <typename T, bool CSMEM, int BOUND>
+static cudaError_t occupancy_t(int nt, int smem, int *blocks) {
+    cudaError_t e = cudaFuncSetAttribute(pk_dp_kernel<T, CSMEM, BOUND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, pk_dp_kernel<T, CSMEM, NT>, NT, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, pk_dp_kernel<T, CSMEM, BOUND>, nt, smem);
 }
 
+#define PK_DISPATCH_NT(FN, TT, CS, ...)                                                         \
+    (nt <= 256 ? FN<TT, CS, 256>(__VA_ARGS__) : nt <= 512 ? FN<TT, CS, 512>(__VA_ARGS__) : FN<TT, CS, 1024>(__VA_ARGS__))
 #define PK_DISPATCH(FN, ...)                                                                    \
-    (prec32 ? (csmem ? (nt == 128   ? FN<float, true, 128>(__VA_ARGS__)                         \
-                        : nt == 256 ? FN<float, true, 256>(__VA_ARGS__)                         \
-                        : nt == 512 ? FN<float, true, 512>(__VA_ARGS__)                         \
-                                    : FN<float, true, 1024>(__VA_ARGS__))                       \
-                     : (nt == 128   ? FN<float, false, 128>(__VA_ARGS__)                        \
-                        : nt == 256 ? FN<float, false, 256>(__VA_ARGS__)                        \
-                        : nt == 512 ? FN<float, false, 512>(__VA_ARGS__)                        \
-                                    : FN<float, false, 1024>(__VA_ARGS__)))                     \
-            : (csmem ? (nt == 128   ? FN<double, true, 128>(__VA_ARGS__)                        \
-                        : nt == 256 ? FN<double, true, 256>(__VA_ARGS__)                        \
-                        : nt == 512 ? FN<double, true, 512>(__VA_ARGS__)                        \
-                                    : FN<double, true, 1024>(__VA_ARGS__))                      \
-                     : (nt == 128   ? FN<double, false, 128>(__VA_ARGS__)                       \
-                        : nt == 256 ? FN<double, false, 256>(__VA_ARGS__)                       \
-                        : nt == 512 ? FN<double, false, 512>(__VA_ARGS__)                       \
-                                    : FN<double, false, 1024>(__VA_ARGS__))))
+    (prec32 ? (csmem ? PK_DISPATCH_NT(FN, float, true, __VA_ARGS__) : PK_DISPATCH_NT(FN, float, false, __VA_ARGS__)) \
+            : (csmem ? PK_DISPATCH_NT(FN, double, true, __VA_ARGS__) : PK_DISPATCH_NT(FN, double, false, __VA_ARGS__)))
 
 static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpArgs args, const pk_params *p) {
     if (fa->ctx != ctx || fb->ctx != ctx) return pk_fail(PK_ERR_INVALID, "forest belongs to another context");
@@ -829,15 +799,35 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
         return pk_fail(PK_ERR_INVALID, "trees too large to stage in shared memory (" + std::to_string(base_smem) +
                                            " bytes needed, " + std::to_string(limit) + " available)");
     const long long c_bytes = ((maxM * (long long)w) + 127) & ~127ll;
-    bool csmem = !ctx->cfg_force_hbm && base_smem + c_bytes <= limit;
-    int smem = (int)(csmem ? base_smem + c_bytes : base_smem);
     args.tree_region = region;
     args.rowinfo_bytes = rowinfo;
 
-    // 256-thread CTAs: 8 warps share one pair (cheap level barriers), several pairs are resident per SM; measured
-    // best on B200 for both storage paths (profiles/r01_tuning.md)
-    int nt = ctx->cfg_threads ? ctx->cfg_threads : 256, per_sm = 0;
-    cudaError_t e = PK_DISPATCH(occupancy_t, smem, &per_sm);
+    // one thread per column of the widest class rectangle (column-stationary mapping)
+    int max_w = 1;
+    for (int c = 0; c < fa->ncls; ++c) max_w = std::max(max_w, std::max(fa->max_cnt[c], fb->max_cnt[c]));
+    if (max_w > 1024)
+        return pk_fail(PK_ERR_INVALID, "a production class has " + std::to_string(max_w) +
+                                           " nodes; this build maps one thread per column and supports up to 1024 "
+                                           "(about 3000 tips)");
+    int nt = std::max(64, (max_w + 31) & ~31);
+    if (ctx->cfg_threads && ctx->cfg_threads >= max_w) nt = ctx->cfg_threads;
+
+    // C in shared memory only when that costs no resident CTAs: with C in a global slab the CTAs of small pairs stay
+    // L2-resident anyway and more pairs per SM hide the level barriers better (measured: profiles/r01_summary.md)
+    bool csmem = false;
+    int smem = (int)base_smem, per_sm = 0;
+    cudaError_t e = PK_DISPATCH(occupancy_t, nt, smem, &per_sm);
+    if (e == cudaSuccess && ctx->cfg_force_hbm != 1 && base_smem + c_bytes <= limit) {
+        int occ_smem = 0;
+        csmem = true;
+        e = PK_DISPATCH(occupancy_t, nt, (int)(base_smem + c_bytes), &occ_smem);
+        if (e == cudaSuccess && (occ_smem >= per_sm || ctx->cfg_force_hbm == 2)) {
+            smem = (int)(base_smem + c_bytes);
+            per_sm = occ_smem;
+        } else {
+            csmem = false;
+        }
+    }
     if (e != cudaSuccess) return pk_fail(PK_ERR_CUDA, std::string("occupancy query: ") + cudaGetErrorString(e));
     if (per_sm < 1) return pk_fail(PK_ERR_CUDA, "kernel does not fit on an SM with the requested configuration");
     if (!csmem && ctx->cfg_ctas > 0) per_sm = std::min(per_sm, ctx->cfg_ctas);
@@ -852,7 +842,7 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
     args.counter = ctx->d_counters + (ctx->counter_next++ % kCounterRing);
     PK_CUDA(cudaMemsetAsync(args.counter, 0, sizeof(unsigned long long), ctx->stream));
     PK_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-    e = PK_DISPATCH(launch_t, args, grid, smem, ctx->stream);
+    e = PK_DISPATCH(launch_t, args, grid, nt, smem, ctx->stream);
     if (e != cudaSuccess) return pk_fail(PK_ERR_CUDA, std::string("DP kernel launch: ") + cudaGetErrorString(e));
     PK_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->ev_valid = true;

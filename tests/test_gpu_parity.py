@@ -72,7 +72,7 @@ def test_reference_unittests_through_tree_objects():
 
 
 @pytest.mark.parametrize("precision", [64, 32])
-@pytest.mark.parametrize("force_hbm", [0, 1])
+@pytest.mark.parametrize("force_hbm", [2, 1, 0])
 def test_random_pairs_against_c_oracle(precision, force_hbm):
     """Ragged sizes, both storage paths (C in shared memory / C in HBM slabs)."""
     get_context().configure(0, 0, force_hbm)
@@ -88,10 +88,12 @@ def test_random_pairs_against_c_oracle(precision, force_hbm):
     want = [c_oracle.kernel(orac[a], orac[b], 0.2, 2.0) for a, b in pairs]
     assert rel(got, want) <= TOL[precision]
     stats = get_context().last_stats()
-    assert stats["path"] == ("hbm" if force_hbm else "smem") and stats["launches"] >= 1
+    assert stats["launches"] >= 1
+    if force_hbm:
+        assert stats["path"] == ("hbm" if force_hbm == 1 else "smem")
 
 
-@pytest.mark.parametrize("threads", [128, 256, 512, 1024])
+@pytest.mark.parametrize("threads", [64, 96, 128, 256, 512, 1024])
 def test_every_cta_shape_gives_the_same_answer(threads):
     nwk = synth.tree_set(6, 120, 900)
     flats = [FlatTree.from_newick(s) for s in nwk]
@@ -99,7 +101,7 @@ def test_every_cta_shape_gives_the_same_answer(threads):
     base = pk.kernel_batch(flats)
     get_context().configure(threads, 0, 0)
     a = pk.kernel_batch(flats)
-    get_context().configure(threads, 2, 1)
+    get_context().configure(threads, 2, 2 if threads <= 256 else 1)
     b = pk.kernel_batch(flats)
     assert rel(a, base) < 1e-13 and rel(b, base) < 1e-13
 
