@@ -333,6 +333,16 @@ def run_ours(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = alg_bytes / (dp_ms_avg / 1e3) / 1e9
+        # DRAM traffic of the same kernel from the committed ncu --set full capture, scaled per DP to this launch
+        traffic, traffic_src = None, None
+        try:
+            cap = json.load(open(os.path.join(REPO, "profiles", "r01_dram_traffic.json")))
+            if cap.get("n_tips") == args.tips and cap.get("precision") == args.precision:
+                traffic = cap["dram_bytes_per_dp"] * stats["dps"]
+                traffic_src = ("profiles/r01_dram_traffic.json: (dram__bytes_read.sum + dram__bytes_write.sum) / %d DPs "
+                               "of one captured Gram launch x %d DPs of this launch" % (cap["dps_in_launch"], stats["dps"]))
+        except (OSError, ValueError, KeyError):
+            pass
         node_pairs_total = None
         line = {
             "metric": "normalised-kernel pair-evals/s (Gram matrix, 500-tip trees)", "value": value,
@@ -347,7 +357,7 @@ def run_ours(args):
             "node_pairs_per_s": (args.tips - 1) ** 2 * value,
             "cells_per_s_rank0": stats["cells"] / (dp_ms_avg / 1e3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "kernel": "pk_dp_kernel (Gram tile launch of rank 0)", "kernel_ms": dp_ms_avg,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "per_dp": "w*(M+R) + 32*(n1+n2) + 8 (SURVEY.md 8d), M and R counted exactly",

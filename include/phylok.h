@@ -146,6 +146,8 @@ int pk_forest_gram_part(pk_ctx *ctx, const pk_forest *f, const pk_params *params
                         int32_t part, int32_t nparts, double *d_out, int64_t ld, double *d_diag);
 /* DPs that pk_forest_gram_part(part, nparts) evaluates (excluding the N diagonal DPs every part repeats) */
 int pk_gram_part_pairs(int32_t n, int32_t tile, int32_t part, int32_t nparts, int64_t *npairs);
+/* the (row-block, column-block) coordinates of that part's tiles; pass tiles = NULL to query the count (host only) */
+int pk_gram_part_tiles(int32_t n, int32_t tile, int32_t part, int32_t nparts, int32_t *tiles, int64_t *ntiles);
 
 /* cross-process sharing of a device buffer (one result matrix on rank 0, written by all ranks over NVLink) */
 int pk_device_alloc(pk_ctx *ctx, size_t bytes, void **d_ptr);

@@ -59,6 +59,7 @@ SIGNATURES = {
     "pk_gram": (ctypes.c_int, [_P, _P, _I32, ctypes.POINTER(pk_params), ctypes.c_int, _P]),
     "pk_forest_gram_part": (ctypes.c_int, [_P, _P, ctypes.POINTER(pk_params), ctypes.c_int, _I32, _I32, _I32, _P, _I64, _P]),
     "pk_gram_part_pairs": (ctypes.c_int, [_I32, _I32, _I32, _I32, ctypes.POINTER(_I64)]),
+    "pk_gram_part_tiles": (ctypes.c_int, [_I32, _I32, _I32, _I32, _P, ctypes.POINTER(_I64)]),
     "pk_device_alloc": (ctypes.c_int, [_P, _SZ, _PP]),
     "pk_device_free": (ctypes.c_int, [_P, _P]),
     "pk_ipc_export": (ctypes.c_int, [_P, _P, _P]),

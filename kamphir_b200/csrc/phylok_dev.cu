@@ -972,6 +972,22 @@ extern "C" int pk_gram_part_pairs(int32_t n, int32_t tile, int32_t part, int32_t
     return gram_tiles(n, tile, part, nparts, nullptr, npairs);
 }
 
+extern "C" int pk_gram_part_tiles(int32_t n, int32_t tile, int32_t part, int32_t nparts, int32_t *tiles, int64_t *ntiles) {
+    if (!ntiles) return pk_fail(PK_ERR_INVALID, "null argument");
+    std::vector<int2> t;
+    int rc = gram_tiles(n, tile, part, nparts, &t, nullptr);
+    if (rc) return rc;
+    if (tiles) {
+        if (*ntiles < (int64_t)t.size()) return pk_fail(PK_ERR_INVALID, "tile buffer too small");
+        for (size_t k = 0; k < t.size(); ++k) {
+            tiles[2 * k] = t[k].x;
+            tiles[2 * k + 1] = t[k].y;
+        }
+    }
+    *ntiles = (int64_t)t.size();
+    return PK_OK;
+}
+
 extern "C" int pk_forest_gram_stats(const pk_forest *f, int32_t tile, int32_t part, int32_t nparts, int64_t counts[4]) {
     if (!f || !counts) return pk_fail(PK_ERR_INVALID, "null argument");
     std::vector<int2> tiles;

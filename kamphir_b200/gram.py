@@ -22,7 +22,7 @@ from . import _lib
 from ._lib import check, pk_params
 from .phylokernel import Forest, get_context
 
-__all__ = ["GramRunner"]
+__all__ = ["GramRunner", "part_tiles", "part_pairs"]
 
 
 class GramRunner(object):
@@ -145,6 +145,24 @@ class GramRunner(object):
                 check(self.L.pk_device_free(self.ctx._h, buf))
         self.d_local = ctypes.c_void_p()
         self.d_diag = ctypes.c_void_p()
+
+
+def part_tiles(n, tile, part, nparts):
+    """(row-block, column-block) coordinates of the Gram tiles that `part` of `nparts` evaluates (host only)."""
+    L = _lib.lib()
+    cnt = ctypes.c_int64(0)
+    check(L.pk_gram_part_tiles(int(n), int(tile), int(part), int(nparts), None, ctypes.byref(cnt)))
+    out = np.zeros((cnt.value, 2), np.int32)
+    if cnt.value:
+        check(L.pk_gram_part_tiles(int(n), int(tile), int(part), int(nparts), out.ctypes.data, ctypes.byref(cnt)))
+    return out
+
+
+def part_pairs(n, tile, part, nparts):
+    """DPs of that part (excluding the diagonal pass every part repeats)."""
+    cnt = ctypes.c_int64(0)
+    check(_lib.lib().pk_gram_part_pairs(int(n), int(tile), int(part), int(nparts), ctypes.byref(cnt)))
+    return cnt.value
 
 
 def _as_tensor(ptr, numel):
