@@ -397,16 +397,29 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 256 ? PK_MINB : 1)) pk_dp_ker
                                 part += v;
                             }
                         }
-                        for (; rr < rend; ++rr, ++rp, cidx += wB) {
-                            const RowRec<T> rec = *rp;
-                            const T g0 = C[rec.q0 == qb0 ? rec.off0 + kb0 : 1];
-                            const T g1 = C[rec.q1 == qb1 ? rec.off1 + kb1 : 1];
-                            const T d0 = rec.a0 - b0, d1 = rec.a1 - b1;
-                            T x1[1] = {(d0 * d0 + d1 * d1) * neg_inv_tau}, e1[1];
-                            pk_gauss<1>(x1, e1, tab_lane, lambda);
-                            const T v = e1[0] * g0 * g1;
-                            C[cidx] = v + sigma;
-                            part += v;
+                        // the last 1..U-1 rows: all their gathers first (one exposed round trip, not one per row)
+                        const int rem = rend - rr;
+                        if (rem > 0) {
+                            T g0[U - 1], g1[U - 1];
+#pragma unroll
+                            for (int u = 0; u < U - 1; ++u) {
+                                if (u < rem) {
+                                    const RowRec<T> rec = rp[u];
+                                    g0[u] = C[rec.q0 == qb0 ? rec.off0 + kb0 : 1];
+                                    g1[u] = C[rec.q1 == qb1 ? rec.off1 + kb1 : 1];
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < U - 1; ++u) {
+                                if (u < rem) {
+                                    const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
+                                    T x1[1] = {(d0 * d0 + d1 * d1) * neg_inv_tau}, e1[1];
+                                    pk_gauss<1>(x1, e1, tab_lane, lambda);
+                                    const T v = e1[0] * g0[u] * g1[u];
+                                    C[cidx + u * wB] = v + sigma;
+                                    part += v;
+                                }
+                            }
                         }
                     }
                     acc += (double)part;
