@@ -81,6 +81,9 @@ int pk_device_count(void);                       /* CUDA devices visible, 0 when
 int pk_tree_from_newick(const char *text, size_t len, int prep_flags, int normalize, int n_states, pk_tree **out);
 int pk_trees_from_newick(const char *text, size_t len, int prep_flags, int normalize, int n_states, int nthreads,
                          pk_tree ***out, int32_t *n_out);
+/* same, for n separate one-tree strings (what a simulator returns, kamphir.py:318-326): no concatenation, no split pass */
+int pk_trees_from_newick_list(const char *const *texts, const size_t *lens, int32_t n, int prep_flags, int normalize,
+                              int n_states, int nthreads, pk_tree ***out, int32_t *n_out);
 void pk_tree_array_free(pk_tree **arr);
 
 /* pk_tree_from_arrays: a tree already walked by the caller (the Python mirror walks Bio.Phylo-like objects in

@@ -34,6 +34,8 @@ SIGNATURES = {
     "pk_tree_from_newick": (ctypes.c_int, [ctypes.c_char_p, _SZ, ctypes.c_int, ctypes.c_int, ctypes.c_int, _PP]),
     "pk_trees_from_newick": (ctypes.c_int, [ctypes.c_char_p, _SZ, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int, ctypes.POINTER(_PP), ctypes.POINTER(_I32)]),
+    "pk_trees_from_newick_list": (ctypes.c_int, [_P, _P, _I32, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.POINTER(_PP), ctypes.POINTER(_I32)]),
     "pk_tree_array_free": (None, [_PP]),
     "pk_tree_from_arrays": (ctypes.c_int, [_I32, _P, _P, _P, _I32, _PP]),
     "pk_tree_free": (None, [_P]),

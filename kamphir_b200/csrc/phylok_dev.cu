@@ -468,6 +468,8 @@ struct pk_ctx {
     size_t tmp_bytes = 0;
     void *h_pinned = nullptr;
     size_t pinned_bytes = 0;
+    std::vector<std::pair<void *, size_t>> pool;   // device buffers of freed forests, reused by later uploads (all work
+                                                   // is ordered on ctx->stream, so reuse needs no extra synchronisation)
     cudaEvent_t ev[2] = {nullptr, nullptr};
     bool ev_valid = false;
     long long launches = 0;
@@ -477,6 +479,7 @@ struct pk_ctx {
 
 struct pk_forest {
     pk_ctx *ctx = nullptr;
+    size_t alloc_bytes = 0;
     int32_t n = 0;
     int32_t precision = 64;
     int32_t ncls = 3;
@@ -547,6 +550,7 @@ extern "C" void pk_ctx_destroy(pk_ctx *ctx) {
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_tmp) cudaFree(ctx->d_tmp);
+    for (auto &b : ctx->pool) cudaFree(b.first);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
@@ -646,6 +650,34 @@ static int ensure_scratch(pk_ctx *ctx, size_t bytes) {
     return PK_OK;
 }
 
+static cudaError_t pool_alloc(pk_ctx *ctx, size_t bytes, void **ptr, size_t *got) {
+    int best = -1;
+    for (size_t k = 0; k < ctx->pool.size(); ++k)
+        if (ctx->pool[k].second >= bytes && ctx->pool[k].second <= 4 * bytes + (1 << 20) &&
+            (best < 0 || ctx->pool[k].second < ctx->pool[best].second))
+            best = (int)k;
+    if (best >= 0) {
+        *ptr = ctx->pool[best].first;
+        *got = ctx->pool[best].second;
+        ctx->pool.erase(ctx->pool.begin() + best);
+        return cudaSuccess;
+    }
+    *got = std::max(bytes, (size_t)1 << 20);
+    return cudaMalloc(ptr, *got);
+}
+
+static void pool_release(pk_ctx *ctx, void *ptr, size_t bytes) {
+    ctx->pool.emplace_back(ptr, bytes);
+    if (ctx->pool.size() > 6) {      // keep the pool small: drop the smallest buffer
+        size_t k = 0;
+        for (size_t i = 1; i < ctx->pool.size(); ++i)
+            if (ctx->pool[i].second < ctx->pool[k].second) k = i;
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(ctx->pool[k].first);
+        ctx->pool.erase(ctx->pool.begin() + k);
+    }
+}
+
 extern "C" int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_t n, int32_t precision, pk_forest **out) {
     if (!ctx || !trees || !out) return pk_fail(PK_ERR_INVALID, "null argument");
     if (n < 1) return pk_fail(PK_ERR_INVALID, "empty tree set");
@@ -696,7 +728,9 @@ extern "C" int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_
         std::copy(t.hist.begin(), t.hist.end(), f->hist.begin() + (size_t)i * t.hist.size());
         off += b;
     }
-    cudaError_t e = cudaMalloc(&f->d_blocks, total + meta_bytes);
+    void *dptr = nullptr;
+    cudaError_t e = pool_alloc(ctx, total + meta_bytes, &dptr, &f->alloc_bytes);
+    f->d_blocks = static_cast<unsigned char *>(dptr);
     if (e == cudaSuccess) {
         f->d_meta = reinterpret_cast<int4 *>(f->d_blocks + total);
         e = cudaMemcpyAsync(f->d_blocks, h, total + meta_bytes, cudaMemcpyHostToDevice, ctx->stream);
@@ -705,6 +739,7 @@ extern "C" int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_
     if (e != cudaSuccess) {
         if (f->d_blocks) cudaFree(f->d_blocks);
         delete f;
+        cudaGetLastError();
         return pk_fail(PK_ERR_CUDA, std::string("pk_forest_upload: ") + cudaGetErrorString(e));
     }
     *out = f;
@@ -714,8 +749,7 @@ extern "C" int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_
 extern "C" void pk_forest_free(pk_forest *f) {
     if (!f) return;
     cudaSetDevice(f->ctx->device);
-    cudaStreamSynchronize(f->ctx->stream);
-    if (f->d_blocks) cudaFree(f->d_blocks);
+    if (f->d_blocks) pool_release(f->ctx, f->d_blocks, f->alloc_bytes);
     delete f;
 }
 

@@ -65,6 +65,15 @@ struct RawTree {
         nchild[par]++;
     }
     size_t size() const { return parent.size(); }
+    void clear() {      // keeps the capacity: one RawTree is reused for every tree a worker parses
+        parent.clear(); first.clear(); last.clear(); next.clear(); nchild.clear();
+        bl.clear(); name_off.clear(); name_len.clear();
+        root = -1;
+    }
+    void reserve(size_t n) {
+        parent.reserve(n); first.reserve(n); last.reserve(n); next.reserve(n); nchild.reserve(n);
+        bl.reserve(n); name_off.reserve(n); name_len.reserve(n);
+    }
 };
 
 inline bool is_punct(char c) {
@@ -75,8 +84,8 @@ inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\n' || c ==
 // One tree from text[b, e) (no terminating ';').  Same token semantics as Biopython's Newick parser:
 // children in input order, '[...]' comments dropped, quoted labels, a ',' at top level creates a new root.
 int parse_one(const char *text, size_t b, size_t e, RawTree &t, std::string &err) {
-    t = RawTree();
-    t.parent.reserve(1024);
+    t.clear();
+    t.reserve((e - b) / 12 + 16);
     int32_t cur = t.add(-1);
     t.root = cur;
     long lp = 0, rp = 0;
@@ -210,18 +219,18 @@ int flatten(const char *text, RawTree &r, int flags, int normalize, int nstates,
     std::vector<int32_t> pre;
     pre.reserve(total);
     std::vector<int32_t> stack;
+    stack.reserve(64);
     auto preorder = [&]() {
         pre.clear();
         stack.clear();
         stack.push_back(root);
-        std::vector<int32_t> kids;
         while (!stack.empty()) {
             int32_t v = stack.back();
             stack.pop_back();
             pre.push_back(v);
-            kids.clear();
-            for (int32_t c = r.first[v]; c >= 0; c = r.next[c]) kids.push_back(c);
-            for (size_t k = kids.size(); k-- > 0;) stack.push_back(kids[k]);
+            const size_t base = stack.size();
+            for (int32_t c = r.first[v]; c >= 0; c = r.next[c]) stack.push_back(c);
+            std::reverse(stack.begin() + base, stack.end());
         }
     };
     preorder();
@@ -238,6 +247,16 @@ int flatten(const char *text, RawTree &r, int flags, int normalize, int nstates,
         std::vector<int32_t> kids;
         for (int32_t v = 0; v < total; ++v) {
             if (r.nchild[v] < 2) continue;
+            if (r.nchild[v] == 2) {        // binary node: swap only when strictly larger first (stable on ties)
+                const int32_t x = r.first[v], y = r.next[x];
+                if (ntip[x] > ntip[y]) {
+                    r.first[v] = y;
+                    r.next[y] = x;
+                    r.next[x] = -1;
+                    r.last[v] = x;
+                }
+                continue;
+            }
             kids.clear();
             for (int32_t c = r.first[v]; c >= 0; c = r.next[c]) kids.push_back(c);
             std::stable_sort(kids.begin(), kids.end(), [&](int32_t a, int32_t b) { return ntip[a] < ntip[b]; });
@@ -520,6 +539,11 @@ extern "C" int pk_tree_from_newick(const char *text, size_t len, int prep_flags,
     return PK_OK;
 }
 
+// shared by the two bulk entry points: tree k is text_of(k)[ranges[k].first, ranges[k].second)
+static int flatten_many(const std::vector<const char *> &bases, const std::vector<std::pair<size_t, size_t>> &ranges,
+                        size_t total_len, int prep_flags, int normalize, int n_states, int nthreads, pk_tree ***out,
+                        int32_t *n_out);
+
 extern "C" int pk_trees_from_newick(const char *text, size_t len, int prep_flags, int normalize, int n_states,
                                     int nthreads, pk_tree ***out, int32_t *n_out) {
     if (!text || !out || !n_out) return pk_fail(PK_ERR_INVALID, "null argument");
@@ -527,11 +551,38 @@ extern "C" int pk_trees_from_newick(const char *text, size_t len, int prep_flags
     *n_out = 0;
     std::vector<std::pair<size_t, size_t>> ranges;
     split_trees(text, len, ranges);
+    std::vector<const char *> bases(ranges.size(), text);
+    return flatten_many(bases, ranges, len, prep_flags, normalize, n_states, nthreads, out, n_out);
+}
+
+extern "C" int pk_trees_from_newick_list(const char *const *texts, const size_t *lens, int32_t n, int prep_flags,
+                                         int normalize, int n_states, int nthreads, pk_tree ***out, int32_t *n_out) {
+    if (!texts || !lens || !out || !n_out) return pk_fail(PK_ERR_INVALID, "null argument");
+    *out = nullptr;
+    *n_out = 0;
+    std::vector<const char *> bases((size_t)std::max(n, 0));
+    std::vector<std::pair<size_t, size_t>> ranges((size_t)std::max(n, 0));
+    size_t total = 0;
+    for (int32_t k = 0; k < n; ++k) {
+        if (!texts[k]) return pk_fail(PK_ERR_INVALID, "null Newick string in list");
+        bases[k] = texts[k];
+        size_t e = lens[k];
+        while (e > 0 && (is_space(texts[k][e - 1]) || texts[k][e - 1] == ';')) --e;   // one tree per string
+        ranges[k] = std::make_pair((size_t)0, e);
+        total += lens[k];
+    }
+    return flatten_many(bases, ranges, total, prep_flags, normalize, n_states, nthreads, out, n_out);
+}
+
+static int flatten_many(const std::vector<const char *> &bases, const std::vector<std::pair<size_t, size_t>> &ranges,
+                        size_t len, int prep_flags, int normalize, int n_states, int nthreads, pk_tree ***out,
+                        int32_t *n_out) {
     const size_t nt = ranges.size();
     pk_tree **arr = new (std::nothrow) pk_tree *[nt + 1]();
     if (!arr) return pk_fail(PK_ERR_NOMEM, "out of memory");
     if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
-    nthreads = (int)std::min<size_t>((size_t)nthreads, std::max<size_t>(1, nt / 8));
+    // a worker per ~64 KB of text: spawning threads costs more than parsing a small batch
+    nthreads = (int)std::min<size_t>((size_t)nthreads, std::max<size_t>(1, std::min<size_t>(nt, len / (64 * 1024))));
     std::atomic<size_t> next{0};
     std::atomic<int> status{PK_OK};
     std::string first_err;
@@ -542,6 +593,7 @@ extern "C" int pk_trees_from_newick(const char *text, size_t len, int prep_flags
         for (;;) {
             size_t k = next.fetch_add(1);
             if (k >= nt || status.load() != PK_OK) break;
+            const char *text = bases[k];
             int rc = parse_one(text, ranges[k].first, ranges[k].second, raw, err);
             if (rc == PK_OK) {
                 arr[k] = new (std::nothrow) pk_tree();

@@ -29,14 +29,21 @@ __all__ = ["PhyloKernel", "FlatTree", "Context", "get_context"]
 class FlatTree(object):
     """Owner of one ``pk_tree*``: a tree flattened to post-order SoA arrays (annotate_tree, phyloK2.py:132-146)."""
 
+    _INFO = ("n_internal", "n_tips", "n_levels", "n_classes", "n_states", "height", "scale")
+
     def __init__(self, handle, recipe):
         self._h = ctypes.c_void_p(handle)
         self._recipe = recipe
-        info = pk_tree_info()
-        check(_lib.lib().pk_tree_get_info(self._h, ctypes.byref(info)))
-        self.n_internal, self.n_tips, self.n_levels = info.n_internal, info.n_tips, info.n_levels
-        self.n_classes, self.n_states = info.n_classes, info.n_states
-        self.height, self.scale = info.height, info.scale
+
+    def __getattr__(self, name):
+        # tree facts are fetched from the library on first use (keeps bulk flattening cheap on the Python side)
+        if name in FlatTree._INFO:
+            info = pk_tree_info()
+            check(_lib.lib().pk_tree_get_info(self._h, ctypes.byref(info)))
+            for k in FlatTree._INFO:
+                self.__dict__[k] = getattr(info, k)
+            return self.__dict__[name]
+        raise AttributeError(name)
 
     # -- constructors --------------------------------------------------------------------------------
     @classmethod
@@ -59,6 +66,22 @@ class FlatTree(object):
                                               int(nthreads), ctypes.byref(arr), ctypes.byref(n)))
         try:
             return [cls(arr[i], ("handle",)) for i in range(n.value)]
+        finally:
+            _lib.lib().pk_tree_array_free(arr)
+
+    @classmethod
+    def many_from_newick_list(cls, texts, prep=PK_PREP_KAMPHIR, normalize="mean", n_states=0, nthreads=0):
+        """One FlatTree per Newick string of ``texts`` (str or bytes), flattened in one library call by worker threads."""
+        raw = [t.encode("utf-8") if isinstance(t, str) else t for t in texts]
+        n = len(raw)
+        ptrs = (ctypes.c_char_p * n)(*raw)
+        lens = (ctypes.c_size_t * n)(*[len(b) for b in raw])
+        arr = ctypes.POINTER(ctypes.c_void_p)()
+        cnt = ctypes.c_int32()
+        check(_lib.lib().pk_trees_from_newick_list(ptrs, lens, n, int(prep), PK_NORM[normalize], int(n_states),
+                                                   int(nthreads), ctypes.byref(arr), ctypes.byref(cnt)))
+        try:
+            return [cls(arr[i], ("newick", raw[i], int(prep), normalize, int(n_states))) for i in range(cnt.value)]
         finally:
             _lib.lib().pk_tree_array_free(arr)
 
@@ -362,6 +385,20 @@ class PhyloKernel(object):
                 bl[i, s] = lens[s]
         return FlatTree.from_arrays(cidx, bl)
 
+    def flatten_list(self, trees, prep=0, normalize='none'):
+        """flatten() for a sequence; runs of Newick strings go through one multi-threaded library call."""
+        trees = list(trees)
+        out = [None] * len(trees)
+        text_idx = [i for i, t in enumerate(trees) if isinstance(t, (str, bytes))]
+        if len(text_idx) > 1:
+            flats = FlatTree.many_from_newick_list([trees[i] for i in text_idx], prep, normalize, self.n_states)
+            for i, f in zip(text_idx, flats):
+                out[i] = f
+        for i, t in enumerate(trees):
+            if out[i] is None:
+                out[i] = self.flatten(t, prep, normalize)
+        return out
+
     def flatten_many(self, newick_text, prep=PK_PREP_KAMPHIR, normalize=None, nthreads=0):
         """Multi-tree Newick text -> list of FlatTree, prepared like kamphir.py:279-282 by default."""
         return FlatTree.many_from_newick(newick_text, prep, self.normalize if normalize is None else normalize,
@@ -389,9 +426,9 @@ class PhyloKernel(object):
 
     def kernel_batch(self, trees_a, trees_b=None, pairs=None):
         """K for many pairs in one launch.  ``pairs`` = [(ia, ib), ...] -> vector; None -> len(a) x len(b) matrix."""
-        fa = [self.flatten(t) for t in trees_a]
+        fa = self.flatten_list(trees_a)
         same = trees_b is None
-        fb = fa if same else [self.flatten(t) for t in trees_b]
+        fb = fa if same else self.flatten_list(trees_b)
         if pairs is None:
             pr = np.stack(np.meshgrid(np.arange(len(fa)), np.arange(len(fb)), indexing='ij'), -1).reshape(-1, 2)
         else:
@@ -414,7 +451,7 @@ class PhyloKernel(object):
         ``kcoal`` and ``score = knorm * kcoal**kadj`` and their mean (``mean_score``).
         """
         fo = self.flatten(obs, PK_PREP_KAMPHIR, self.normalize)
-        fs = [self.flatten(s, PK_PREP_KAMPHIR, self.normalize) for s in sims]
+        fs = self.flatten_list(sims, PK_PREP_KAMPHIR, self.normalize)
         n = len(fs)
         k, d, kh = np.empty(n), np.empty(n), np.empty(n)
         ref = ctypes.c_double(float('nan') if ref_denom is None else float(ref_denom))
@@ -434,7 +471,7 @@ class PhyloKernel(object):
 
     def gram(self, trees, normalised=True):
         """All-pairs matrix over ``trees`` (FlatTree / Newick / tree objects): raw K or K/sqrt(K_ii K_jj)."""
-        ft = [self.flatten(t, PK_PREP_KAMPHIR, self.normalize) for t in trees]
+        ft = self.flatten_list(trees, PK_PREP_KAMPHIR, self.normalize)
         n = len(ft)
         out = np.empty((n, n), np.float64)
         arr = (ctypes.c_void_p * n)(*[t._h for t in ft])

@@ -150,3 +150,15 @@ def test_flat_tree_pickles():
             assert np.array_equal(x, y)
     pk = pickle.loads(pickle.dumps(PhyloKernel(decayFactor=0.3, precision=32)))
     assert pk.decayFactor == 0.3 and pk.precision == 32
+
+
+def test_list_api_matches_single_calls():
+    nwk = synth.tree_set(40, 25, 77) + ["  " + synth.kingman_newick(9, 3) + "  \n"]
+    many = FlatTree.many_from_newick_list(nwk, 3, "mean", 0, 3)
+    assert len(many) == len(nwk)
+    for ft, s in zip(many, nwk):
+        one = FlatTree.from_newick(s, 3, "mean")
+        for x, y in zip(ft.export(), one.export()):
+            assert np.array_equal(x, y)
+    with pytest.raises(ValueError):
+        FlatTree.many_from_newick_list(nwk[:3] + ["((a:1,b:2,c:3):1,d:1);"], 3, "mean")
