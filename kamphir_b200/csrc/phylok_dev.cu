@@ -186,7 +186,7 @@ struct __align__(16) LevelDesc {
 // balanced level barriers -- and a CTA has as many warps as the widest class needs (6 for 500-tip trees), several CTAs
 // (pairs) being resident per SM.
 template <typename T, bool CSMEM, int BOUND>     // BOUND: upper bound of the CTA size (sets the register budget)
-__global__ void __launch_bounds__(BOUND, (BOUND <= 256 ? PK_MINB : 1)) pk_dp_kernel(const DpArgs a) {
+__global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_MINB : 1)) pk_dp_kernel(const DpArgs a) {
     const int NT = blockDim.x, NW = NT >> 5;       // any multiple of 32 up to BOUND
     constexpr int U = PK_UNROLL;   // rows in flight per lane
     extern __shared__ __align__(128) unsigned char smem[];
@@ -808,8 +808,12 @@ static cudaError_t occupancy_t(int nt, int smem, int *blocks) {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, pk_dp_kernel<T, CSMEM, BOUND>, nt, smem);
 }
 
+// register budgets: <= 224 threads: 72 registers (4 CTAs of 7 warps per SM), <= 256: 80, <= 512: 128, else 64
 #define PK_DISPATCH_NT(FN, TT, CS, ...)                                                         \
-    (nt <= 256 ? FN<TT, CS, 256>(__VA_ARGS__) : nt <= 512 ? FN<TT, CS, 512>(__VA_ARGS__) : FN<TT, CS, 1024>(__VA_ARGS__))
+    (nt <= 224   ? FN<TT, CS, 224>(__VA_ARGS__)                                                 \
+     : nt <= 256 ? FN<TT, CS, 256>(__VA_ARGS__)                                                 \
+     : nt <= 512 ? FN<TT, CS, 512>(__VA_ARGS__)                                                 \
+                 : FN<TT, CS, 1024>(__VA_ARGS__))
 #define PK_DISPATCH(FN, ...)                                                                    \
     (prec32 ? (csmem ? PK_DISPATCH_NT(FN, float, true, __VA_ARGS__) : PK_DISPATCH_NT(FN, float, false, __VA_ARGS__)) \
             : (csmem ? PK_DISPATCH_NT(FN, double, true, __VA_ARGS__) : PK_DISPATCH_NT(FN, double, false, __VA_ARGS__)))
