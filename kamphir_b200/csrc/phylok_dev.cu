@@ -40,7 +40,7 @@
 // ---------------------------------------------------------------------------------------------------
 struct DpArgs {
     const unsigned char *blocksA;   // packed tree blocks of forest A
-    const int4 *metaA;              // per tree: {offset / 16, bytes, n, nlev}
+    const int4 *metaA;              // per tree two records: row part, column part: {offset / 16, bytes, n, nlev}
     const unsigned char *blocksB;
     const int4 *metaB;
     int mode;                       // 0: explicit pair list, 1: Gram tiles, 2: diagonal (i,i)
@@ -56,8 +56,9 @@ struct DpArgs {
     void *scratch;                  // HBM path: per-CTA C slabs
     long long slab_elems;
     unsigned long long *counter;    // work counter
-    int tree_region;                // bytes reserved per staged tree block in shared memory
-    int rowinfo_bytes;
+    int tree_region;                // shared-memory bytes reserved for the staged ROW part
+    int col_region;                 // ... and for the staged COLUMN part
+    int rowinfo_bytes;              // row offsets
     double exp_tab[64];             // lambda * 2^(j/64), j = 0..63 (fp64 Gaussian)
 };
 
@@ -146,18 +147,19 @@ __device__ __forceinline__ void pk_gauss(const float (&x)[U], float (&out)[U], c
 // stays away from 0/1 by 0.5/b, which the +0.5 guarantees); the kernel's uniform per-level bookkeeping uses it
 __device__ __forceinline__ int pk_div(int a, int b) { return __float2int_rz(__fdividef((float)a + 0.5f, (float)b)); }
 
-// per row of the row tree: branch lengths and, per child slot, the child's class + 1 (0 = tip) and the offset of the
-// child's row in the compact C layout
+// per row of the row tree: branch lengths, per child slot the offset of the child's stored row in C, the offset that
+// turns a column position into this row's stored cell, and three packed bytes: class + 1 of child 0, of child 1
+// (0 = tip) and the row's parent code
 template <typename T>
 struct __align__(16) RowRec {
     T a0, a1;
-    int q0, off0, q1, off1;
+    int off0, off1, st_off, packed;
     char pad[32 - 2 * sizeof(T) - 16];
 };
 template <>
 struct __align__(16) RowRec<double> {
     double a0, a1;
-    int q0, off0, q1, off1;
+    int off0, off1, st_off, packed;
 };
 
 // one (level, class) rectangle of the wavefront, precomputed per pair so the warps only read it
@@ -166,7 +168,7 @@ struct __align__(16) LevelDesc {
     int rows;       // rows at this level in this class (0: empty, skipped)
     int wB;         // columns = nodes of the column tree in this class
     int colbase;    // first column (kernel order in the column tree)
-    int cbase;      // C index of (row r0, column 0)
+    int cbase;      // unused (rows carry their own C offsets)
     int flags;      // bit 8: last rectangle of its level (a barrier follows); bit 9: all-tip-children class
     int pad0, pad1;
 };
@@ -192,17 +194,17 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ long long s_work[2];
-    __shared__ int s_coff[PK_MAX_CLASSES + 1];
     __shared__ int s_cntB[PK_MAX_CLASSES];
     __shared__ double s_part[32];
     __shared__ __align__(16) LevelDesc s_desc[PK_DESC_MAX];
     __shared__ __align__(16) double s_tab[sizeof(T) == 8 ? PK_EXP_TAB * PK_EXP_REP : 2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned char *sA = smem;
-    unsigned char *sB = smem + a.tree_region;
-    RowRec<T> *rowrec = reinterpret_cast<RowRec<T> *>(smem + 2 * (size_t)a.tree_region);
-    T *C = CSMEM ? reinterpret_cast<T *>(smem + 2 * (size_t)a.tree_region + a.rowinfo_bytes)
+    unsigned char *sA = smem;                                  // ROW part of the row tree (its records are patched in place)
+    unsigned char *sB = smem + a.tree_region;                  // COLUMN part of the column tree
+    const size_t info_at = (size_t)a.tree_region + a.col_region;
+    int *rowoff = reinterpret_cast<int *>(smem + info_at);
+    T *C = CSMEM ? reinterpret_cast<T *>(smem + info_at + a.rowinfo_bytes)
                  : reinterpret_cast<T *>(a.scratch) + (size_t)blockIdx.x * (size_t)a.slab_elems;
 
     if (tid == 0) mbar_init(&s_bar, 1);
@@ -238,11 +240,13 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
         } else {
             ia = ib = (int)w;
         }
-        const int4 mA = a.metaA[ia], mB = a.metaB[ib];
+        const int4 mA = a.metaA[2 * ia], mB = a.metaB[2 * ib];
         const bool swap = mA.w > mB.w;   // rows come from the tree with fewer wavefront levels (K is symmetric)
-        const unsigned char *srcR = swap ? a.blocksB + (size_t)mB.x * 16 : a.blocksA + (size_t)mA.x * 16;
-        const unsigned char *srcC = swap ? a.blocksA + (size_t)mA.x * 16 : a.blocksB + (size_t)mB.x * 16;
-        const uint32_t bytesR = swap ? mB.y : mA.y, bytesC = swap ? mA.y : mB.y;
+        const int4 mR = swap ? mB : mA;                                      // row part of the row tree
+        const int4 mC = swap ? a.metaA[2 * ia + 1] : a.metaB[2 * ib + 1];    // column part of the column tree
+        const unsigned char *srcR = (swap ? a.blocksB : a.blocksA) + (size_t)mR.x * 16;
+        const unsigned char *srcC = (swap ? a.blocksA : a.blocksB) + (size_t)mC.x * 16;
+        const uint32_t bytesR = mR.y, bytesC = mC.y;
 
         // ---- stage both node blocks with TMA bulk copies ---------------------------------------
         if (tid == 0) {
@@ -255,46 +259,58 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
 
         const int *hA = reinterpret_cast<const int *>(sA);
         const int *hB = reinterpret_cast<const int *>(sB);
-        const int nA = hA[0], ncls = hA[1], nlevA = hA[2];
+        const int nA = hA[0], ncls = hA[1], nlevA = hA[2], npc = 2 * ncls + 2;
         const unsigned long long tipmask = (unsigned)hA[12] | ((unsigned long long)(unsigned)hA[13] << 32);
-        const int *clsA = reinterpret_cast<const int *>(sA + hA[4]);
         const int *lvlA = reinterpret_cast<const int *>(sA + hA[5]);
-        const T *a0p = reinterpret_cast<const T *>(sA + hA[6]);
-        const T *a1p = reinterpret_cast<const T *>(sA + hA[7]);
-        const int *codeA0 = reinterpret_cast<const int *>(sA + hA[8]);
-        const int *codeA1 = reinterpret_cast<const int *>(sA + hA[9]);
+        RowRec<T> *rowrec = reinterpret_cast<RowRec<T> *>(sA + hA[6]);
         const int *clsB = reinterpret_cast<const int *>(sB + hB[4]);
+        const int *gstB = reinterpret_cast<const int *>(sB + hB[5]);
         const T *b0p = reinterpret_cast<const T *>(sB + hB[6]);
         const T *b1p = reinterpret_cast<const T *>(sB + hB[7]);
         const int *codeB0 = reinterpret_cast<const int *>(sB + hB[8]);
         const int *codeB1 = reinterpret_cast<const int *>(sB + hB[9]);
+        const int *pcB = reinterpret_cast<const int *>(sB + hB[10]);
 
-        // ---- compact C layout (cells hold sigma + C, the factor a parent multiplies by): cell 0 = tip x tip,
-        //      cell 1 = 1 (no match), then one rectangle per class
+        // ---- compact C layout.  Cells hold sigma + C (the factor a parent multiplies by).  Cell 0 = tip x tip, cell 1 = 1
+        //      (child productions differ).  A cell (i, j) is only ever read by the cell of the two parents, and only when
+        //      i and j have the same parent code; columns are ordered by (class, parent code), so row i stores just the
+        //      contiguous column group with its own parent code: R cells per pair instead of M.
+        if (tid < ncls) s_cntB[tid] = clsB[tid + 1] - clsB[tid];
         if (tid == 0) {
-            int off = 2;
-            for (int c = 0; c < ncls; ++c) {
-                const int wB = clsB[c + 1] - clsB[c];
-                s_cntB[c] = wB;
-                s_coff[c] = off;
-                off += (clsA[c + 1] - clsA[c]) * wB;
-            }
-            s_coff[ncls] = off;
             C[0] = sigma + lambda;   // tip x tip child factor (phyloK2.py:194-196)
             C[1] = (T)1;             // factor of a child slot whose productions differ (phyloK2.py:191-192)
         }
+        // row offsets: exclusive scan of the stored row lengths, by warp 0 (32 rows per step, running carry)
+        if (warp == 0) {
+            int carry = 2;
+            for (int base = 0; base < nA; base += 32) {
+                const int r = base + lane;
+                int len = 0;
+                if (r < nA) {
+                    const int pk = rowrec[r].packed;
+                    const int g = ((pk >> 24) & 0xff) * npc + ((pk >> 16) & 0xff);
+                    len = gstB[g + 1] - gstB[g];
+                }
+                int incl = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                if (r < nA) rowoff[r] = carry + incl - len;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
         __syncthreads();
-        for (int r = tid; r < nA; r += NT) {
-            const int c0 = codeA0[r], c1 = codeA1[r];
-            const int q0 = c0 >> 24, q1 = c1 >> 24;
-            RowRec<T> rec;
-            rec.a0 = a0p[r];
-            rec.a1 = a1p[r];
-            rec.q0 = q0;
-            rec.off0 = q0 ? s_coff[q0 - 1] + (c0 & 0xffffff) * s_cntB[q0 - 1] : 0;
-            rec.q1 = q1;
-            rec.off1 = q1 ? s_coff[q1 - 1] + (c1 & 0xffffff) * s_cntB[q1 - 1] : 0;
-            rowrec[r] = rec;
+        for (int r = tid; r < nA; r += NT) {      // patch the staged records with this pair's C offsets
+            RowRec<T> *rec = rowrec + r;
+            const int pk = rec->packed;
+            const int c = (pk >> 24) & 0xff, p = (pk >> 16) & 0xff;
+            const int o0 = (pk & 0xff) ? rowoff[rec->off0] : 0;
+            const int o1 = (pk & 0xff00) ? rowoff[rec->off1] : 0;
+            rec->off0 = o0;
+            rec->off1 = o1;
+            rec->st_off = rowoff[r] - (gstB[c * npc + p] - clsB[c]);       // + column position in the class = stored cell
         }
 
         // ---- wavefront over the row tree's levels, a batch of levels at a time -------------------------
@@ -312,7 +328,6 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
                     d.r0 = r0; d.rows = 0; d.wB = wB; d.colbase = clsB[c]; d.cbase = 0; d.flags = 0; d.pad0 = d.pad1 = 0;
                     if (rows > 0 && wB > 0) {
                         d.rows = rows;
-                        d.cbase = s_coff[c] + (r0 - clsA[c]) * wB;
                         d.flags = ((tipmask >> c) & 1ull) ? 512 : 0;
                         last = c;
                     }
@@ -329,14 +344,14 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
                 if (jb < wB) {
                     const int col = d.colbase + jb;
                     const T b0 = b0p[col], b1 = b1p[col];
+                    const int pkey = pcB[col] << 16;              // this column's parent code, aligned with rec.packed
                     const int rend = d.r0 + d.rows;
-                    int cidx = d.cbase + jb;                     // this thread's cell in row r0
                     const RowRec<T> *rp = rowrec + d.r0;
                     T part = (T)0;
                     int rr = d.r0;
                     if (d.flags & 512) {
                         // class whose nodes have two tip children: no child cells, f0*f1 = (sigma+lambda)^2
-                        for (; rr + U <= rend; rr += U, rp += U, cidx += U * wB) {
+                        for (; rr + U <= rend; rr += U, rp += U) {
                             T x[U], ev[U];
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
@@ -347,21 +362,21 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
                                 const T v = ev[u] * tip2;
-                                C[cidx + u * wB] = v + sigma;
+                                if ((rp[u].packed & 0xff0000) == pkey) C[rp[u].st_off + jb] = v + sigma;
                                 part += v;
                             }
                         }
-                        for (; rr < rend; ++rr, ++rp, cidx += wB) {
+                        for (; rr < rend; ++rr, ++rp) {
                             const T d0 = rp->a0 - b0, d1 = rp->a1 - b1;
                             T x1[1] = {(d0 * d0 + d1 * d1) * neg_inv_tau}, e1[1];
                             pk_gauss<1>(x1, e1, tab_lane, lambda);
                             const T v = e1[0] * tip2;
-                            C[cidx] = v + sigma;
+                            if ((rp->packed & 0xff0000) == pkey) C[rp->st_off + jb] = v + sigma;
                             part += v;
                         }
                     } else {
                         const int cb0 = codeB0[col], cb1 = codeB1[col];
-                        const int qb0 = cb0 >> 24, kb0 = cb0 & 0xffffff, qb1 = cb1 >> 24, kb1 = cb1 & 0xffffff;
+                        const int qb0 = cb0 >> 24, kb0 = cb0 & 0xffffff, qb1 = (cb1 >> 24) << 8, kb1 = cb1 & 0xffffff;
                         // software pipeline: the child-cell gathers of the NEXT group of U rows are issued before the
                         // Gaussians of the current group, so their (L2/HBM) latency is covered
                         T f0[U], f1[U];
@@ -369,31 +384,33 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
                                 const RowRec<T> rec = rp[u];
-                                f0[u] = C[rec.q0 == qb0 ? rec.off0 + kb0 : 1];
-                                f1[u] = C[rec.q1 == qb1 ? rec.off1 + kb1 : 1];
+                                f0[u] = C[(rec.packed & 0xff) == qb0 ? rec.off0 + kb0 : 1];
+                                f1[u] = C[(rec.packed & 0xff00) == qb1 ? rec.off1 + kb1 : 1];
                             }
                         }
-                        for (; rr + U <= rend; rr += U, rp += U, cidx += U * wB) {
+                        for (; rr + U <= rend; rr += U, rp += U) {
                             T x[U], ev[U], g[U];
+                            int so[U];                              // where each row's cell is stored, -1: never read
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
                                 const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
                                 x[u] = (d0 * d0 + d1 * d1) * neg_inv_tau;
                                 g[u] = f0[u] * f1[u];
+                                so[u] = (rp[u].packed & 0xff0000) == pkey ? rp[u].st_off + jb : -1;
                             }
                             if (rr + 2 * U <= rend) {
 #pragma unroll
                                 for (int u = 0; u < U; ++u) {
                                     const RowRec<T> rec = rp[U + u];
-                                    f0[u] = C[rec.q0 == qb0 ? rec.off0 + kb0 : 1];
-                                    f1[u] = C[rec.q1 == qb1 ? rec.off1 + kb1 : 1];
+                                    f0[u] = C[(rec.packed & 0xff) == qb0 ? rec.off0 + kb0 : 1];
+                                    f1[u] = C[(rec.packed & 0xff00) == qb1 ? rec.off1 + kb1 : 1];
                                 }
                             }
                             pk_gauss<U>(x, ev, tab_lane, lambda);
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
                                 const T v = ev[u] * g[u];
-                                C[cidx + u * wB] = v + sigma;
+                                if (so[u] >= 0) C[so[u]] = v + sigma;
                                 part += v;
                             }
                         }
@@ -405,8 +422,8 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
                             for (int u = 0; u < U - 1; ++u) {
                                 if (u < rem) {
                                     const RowRec<T> rec = rp[u];
-                                    g0[u] = C[rec.q0 == qb0 ? rec.off0 + kb0 : 1];
-                                    g1[u] = C[rec.q1 == qb1 ? rec.off1 + kb1 : 1];
+                                    g0[u] = C[(rec.packed & 0xff) == qb0 ? rec.off0 + kb0 : 1];
+                                    g1[u] = C[(rec.packed & 0xff00) == qb1 ? rec.off1 + kb1 : 1];
                                 }
                             }
 #pragma unroll
@@ -416,7 +433,7 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
                                     T x1[1] = {(d0 * d0 + d1 * d1) * neg_inv_tau}, e1[1];
                                     pk_gauss<1>(x1, e1, tab_lane, lambda);
                                     const T v = e1[0] * g0[u] * g1[u];
-                                    C[cidx + u * wB] = v + sigma;
+                                    if ((rp[u].packed & 0xff0000) == pkey) C[rp[u].st_off + jb] = v + sigma;
                                     part += v;
                                 }
                             }
@@ -486,8 +503,10 @@ struct pk_forest {
     unsigned char *d_blocks = nullptr;
     int4 *d_meta = nullptr;
     size_t bytes = 0;
-    int32_t max_block = 0, max_n = 0;
+    int32_t max_rowpart = 0, max_colpart = 0, max_n = 0;
     std::vector<int32_t> max_cnt;   // per class, max node count over the trees
+    std::vector<int32_t> gcnt;      // [n][ncls * npc] nodes per (class, parent code) group
+    std::vector<int32_t> max_gcnt;  // [ncls * npc] max over the trees
     std::vector<int32_t> cnt;       // [n][ncls]
     std::vector<int64_t> hist;      // [n][ncls*2*(ncls+1)]
     std::vector<int32_t> nint;      // [n]
@@ -690,9 +709,10 @@ extern "C" int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_
     for (int32_t i = 0; i < n; ++i) {
         if (!trees[i]) return pk_fail(PK_ERR_INVALID, "null tree in set");
         if (trees[i]->ncls != ncls) return pk_fail(PK_ERR_INVALID, "trees use different production class schemes");
-        total += pk_block_bytes(*trees[i], precision);
+        total += pk_rowpart_bytes(*trees[i], precision) + pk_colpart_bytes(*trees[i], precision);
     }
     if (total / 16 > 0x7fffffffull) return pk_fail(PK_ERR_INVALID, "tree set too large for one forest");
+    const int npc = 2 * ncls + 2;
     pk_forest *f = new pk_forest();
     f->ctx = ctx;
     f->n = n;
@@ -701,9 +721,11 @@ extern "C" int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_
     f->bytes = total;
     f->max_cnt.assign(ncls, 0);
     f->cnt.resize((size_t)n * ncls);
+    f->gcnt.resize((size_t)n * ncls * npc);
+    f->max_gcnt.assign((size_t)ncls * npc, 0);
     f->hist.resize((size_t)n * ncls * 2 * (ncls + 1));
     f->nint.resize(n);
-    const size_t meta_bytes = sizeof(int4) * (size_t)n;
+    const size_t meta_bytes = sizeof(int4) * 2 * (size_t)n;
     rc = ensure_pinned(ctx, total + meta_bytes);
     if (rc) {
         delete f;
@@ -714,10 +736,13 @@ extern "C" int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_
     size_t off = 0;
     for (int32_t i = 0; i < n; ++i) {
         const pk_tree &t = *trees[i];
-        const size_t b = pk_block_bytes(t, precision);
-        pk_block_pack(t, precision, h + off);
-        hmeta[i] = make_int4((int)(off / 16), (int)b, t.n, t.nlev);
-        f->max_block = std::max<int32_t>(f->max_block, (int32_t)b);
+        const size_t rb = pk_rowpart_bytes(t, precision), cb = pk_colpart_bytes(t, precision);
+        pk_rowpart_pack(t, precision, h + off);
+        pk_colpart_pack(t, precision, h + off + rb);
+        hmeta[2 * i] = make_int4((int)(off / 16), (int)rb, t.n, t.nlev);            // row part
+        hmeta[2 * i + 1] = make_int4((int)((off + rb) / 16), (int)cb, t.n, t.nlev);   // column part
+        f->max_rowpart = std::max<int32_t>(f->max_rowpart, (int32_t)rb);
+        f->max_colpart = std::max<int32_t>(f->max_colpart, (int32_t)cb);
         f->max_n = std::max(f->max_n, t.n);
         f->nint[i] = t.n;
         for (int c = 0; c < ncls; ++c) {
@@ -725,8 +750,13 @@ extern "C" int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_
             f->cnt[(size_t)i * ncls + c] = cnt;
             f->max_cnt[c] = std::max(f->max_cnt[c], cnt);
         }
+        for (int g = 0; g < ncls * npc; ++g) {
+            const int cnt = t.gstart[g + 1] - t.gstart[g];
+            f->gcnt[(size_t)i * ncls * npc + g] = cnt;
+            f->max_gcnt[g] = std::max(f->max_gcnt[g], cnt);
+        }
         std::copy(t.hist.begin(), t.hist.end(), f->hist.begin() + (size_t)i * t.hist.size());
-        off += b;
+        off += rb + cb;
     }
     void *dptr = nullptr;
     cudaError_t e = pool_alloc(ctx, total + meta_bytes, &dptr, &f->alloc_bytes);
@@ -755,7 +785,7 @@ extern "C" void pk_forest_free(pk_forest *f) {
 
 extern "C" int pk_forest_bytes(const pk_forest *f, int64_t *bytes) {
     if (!f || !bytes) return pk_fail(PK_ERR_INVALID, "null argument");
-    *bytes = (int64_t)(f->bytes + sizeof(int4) * (size_t)f->n);
+    *bytes = (int64_t)(f->bytes + sizeof(int4) * 2 * (size_t)f->n);
     return PK_OK;
 }
 
@@ -839,18 +869,34 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
     args.sigma = p->sigma;
     for (int j = 0; j < 64; ++j) args.exp_tab[j] = p->decay * std::exp2((double)j / 64.0);
 
-    // upper bound of the compact C size over all pairs of the two forests
-    long long maxM = 2;   // cell 0 (tip x tip factor) and cell 1 (no-match factor) precede the class rectangles
-    for (int c = 0; c < fa->ncls; ++c) maxM += (long long)fa->max_cnt[c] * fb->max_cnt[c];
-    const int region = (std::max(fa->max_block, fb->max_block) + 127) & ~127;
-    const int rowinfo = ((std::max(fa->max_n, fb->max_n) * 32) + 127) & ~127;
-    const long long base_smem = 2ll * region + rowinfo;
-    const long long limit = ctx->smem_optin - 16384;   // static shared memory (table, level descriptors, ...)   // static shared memory of the kernel
+    // Upper bound of the stored C cells over all pairs: row i keeps one cell per column of its own (class, parent code)
+    // group, so a pair stores sum_g rows_g * cols_g cells; bound the columns by the per-group maximum over both forests.
+    long long maxM = 0;
+    {
+        const int ng = fa->ncls * (2 * fa->ncls + 2);
+        std::vector<long long> gmax(ng);
+        for (int g = 0; g < ng; ++g) gmax[g] = std::max(fa->max_gcnt[g], fb->max_gcnt[g]);
+        const pk_forest *fs[2] = {fa, fb};
+        for (int k = 0; k < (fa == fb ? 1 : 2); ++k)
+            for (int32_t i = 0; i < fs[k]->n; ++i) {
+                long long m = 0;
+                for (int g = 0; g < ng; ++g) m += (long long)fs[k]->gcnt[(size_t)i * ng + g] * gmax[g];
+                maxM = std::max(maxM, m);
+            }
+        maxM += 2;   // cell 0 (tip x tip factor) and cell 1 (no-match factor) precede the rows
+    }
+    const int region_r = (std::max(fa->max_rowpart, fb->max_rowpart) + 127) & ~127;
+    const int region_c = (std::max(fa->max_colpart, fb->max_colpart) + 127) & ~127;
+    const int max_n = std::max(fa->max_n, fb->max_n);
+    const int rowinfo = ((max_n * 4) + 127) & ~127;                          // row offsets
+    const long long base_smem = (long long)region_r + region_c + rowinfo;
+    const long long limit = ctx->smem_optin - 16384;   // static shared memory (table, level descriptors, ...)
     if (base_smem > limit)
         return pk_fail(PK_ERR_INVALID, "trees too large to stage in shared memory (" + std::to_string(base_smem) +
                                            " bytes needed, " + std::to_string(limit) + " available)");
     const long long c_bytes = ((maxM * (long long)w) + 127) & ~127ll;
-    args.tree_region = region;
+    args.tree_region = region_r;
+    args.col_region = region_c;
     args.rowinfo_bytes = rowinfo;
 
     // one thread per column of the widest class rectangle (column-stationary mapping)

@@ -441,6 +441,28 @@ int pk_tree_finish(pk_tree &t) {
         t.order[row] = i;
         t.rank[i] = row - t.cls_start[t.cls[i]];
     }
+    // parent codes and the column order (class, parent code, post-order)
+    const int npc = 2 * ncls + 2;
+    t.pcode.assign(n, 0);
+    for (int32_t i = 0; i < n; ++i)
+        for (int s = 0; s < 2; ++s) {
+            int32_t c = t.cidx[2 * (size_t)i + s];
+            if (c >= 0) t.pcode[c] = (uint8_t)((t.cls[i] + 1) * 2 + s);
+        }
+    t.gstart.assign((size_t)ncls * npc + 1, 0);
+    for (int32_t i = 0; i < n; ++i) t.gstart[(size_t)t.cls[i] * npc + t.pcode[i] + 1]++;
+    for (size_t k = 1; k < t.gstart.size(); ++k) t.gstart[k] += t.gstart[k - 1];
+    t.colorder.assign(n, 0);
+    t.krank.assign(n, 0);
+    {
+        std::vector<int32_t> fill(t.gstart.begin(), t.gstart.end() - 1);
+        for (int32_t i = 0; i < n; ++i) {
+            const size_t g = (size_t)t.cls[i] * npc + t.pcode[i];
+            const int32_t col = fill[g]++;
+            t.colorder[col] = i;
+            t.krank[i] = col - t.gstart[g];
+        }
+    }
     t.hist.assign((size_t)ncls * 2 * (ncls + 1), 0);
     for (int32_t i = 0; i < n; ++i)
         for (int s = 0; s < 2; ++s) {
@@ -456,23 +478,36 @@ int pk_tree_finish(pk_tree &t) {
 // ---------------------------------------------------------------------------------------------------
 static inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-size_t pk_block_bytes(const pk_tree &t, int precision) {
-    size_t w = precision == 32 ? 4 : 8;
+size_t pk_rowpart_bytes(const pk_tree &t, int /*precision*/) {
     size_t b = PK_HDR_INTS * 4;
     b += align16((size_t)(t.ncls + 1) * 4);
     b += align16((size_t)t.ncls * (t.nlev + 1) * 4);
-    b += 2 * align16((size_t)t.n * w);
-    b += 2 * align16((size_t)t.n * 4);
+    b += (size_t)t.n * 32;                                   // one 32-byte row record per internal node
     return b;
 }
 
-void pk_block_pack(const pk_tree &t, int precision, unsigned char *dst) {
+size_t pk_colpart_bytes(const pk_tree &t, int precision) {
     const size_t w = precision == 32 ? 4 : 8;
-    const size_t total = pk_block_bytes(t, precision);
+    const size_t npc = 2 * (size_t)t.ncls + 2;
+    size_t b = PK_HDR_INTS * 4;
+    b += align16((size_t)(t.ncls + 1) * 4);
+    b += align16(((size_t)t.ncls * npc + 1) * 4);
+    b += 2 * align16((size_t)t.n * w);
+    b += 3 * align16((size_t)t.n * 4);
+    return b;
+}
+
+static void put_real(unsigned char *dst, size_t w, int32_t k, double v) {
+    if (w == 8) reinterpret_cast<double *>(dst)[k] = v;
+    else reinterpret_cast<float *>(dst)[k] = (float)v;
+}
+
+void pk_rowpart_pack(const pk_tree &t, int precision, unsigned char *dst) {
+    const size_t total = pk_rowpart_bytes(t, precision);
     std::memset(dst, 0, total);
     int32_t *hdr = reinterpret_cast<int32_t *>(dst);
     size_t off = PK_HDR_INTS * 4;
-    hdr[0] = t.n; hdr[1] = t.ncls; hdr[2] = t.nlev; hdr[3] = (int32_t)total; hdr[10] = t.ntips; hdr[11] = precision;
+    hdr[0] = t.n; hdr[1] = t.ncls; hdr[2] = t.nlev; hdr[3] = (int32_t)total; hdr[11] = precision;
     {   // classes whose nodes all have two tip children (their cells need no child-cell gathers); bit c of hdr[12..13]
         uint64_t mask = 0;
         for (int c = 0; c < t.ncls; ++c) {
@@ -492,24 +527,67 @@ void pk_block_pack(const pk_tree &t, int precision, unsigned char *dst) {
     hdr[5] = (int32_t)off;
     std::memcpy(dst + off, t.lvl.data(), t.lvl.size() * 4);
     off += align16((size_t)t.ncls * (t.nlev + 1) * 4);
+    hdr[6] = (int32_t)off;                                   // row records
+    std::vector<int32_t> rowof(t.n);                         // post-order index -> kernel row
+    for (int32_t row = 0; row < t.n; ++row) rowof[t.order[row]] = row;
+    // record (32 bytes): a0, a1 (real), then 4 ints: kernel row of child 0, of child 1 (the kernel replaces them by the
+    // children's C offsets), 0 (becomes the row's store offset), packed = q0 | q1 << 8 | parent code << 16 | class << 24
+    // with q = class + 1 of the child, 0 for a tip
+    for (int32_t row = 0; row < t.n; ++row) {
+        const int32_t i = t.order[row];
+        unsigned char *rec = dst + off + (size_t)row * 32;
+        int32_t *ints;
+        if (precision == 32) {
+            reinterpret_cast<float *>(rec)[0] = (float)t.bl[2 * (size_t)i];
+            reinterpret_cast<float *>(rec)[1] = (float)t.bl[2 * (size_t)i + 1];
+            ints = reinterpret_cast<int32_t *>(rec + 8);
+        } else {
+            reinterpret_cast<double *>(rec)[0] = t.bl[2 * (size_t)i];
+            reinterpret_cast<double *>(rec)[1] = t.bl[2 * (size_t)i + 1];
+            ints = reinterpret_cast<int32_t *>(rec + 16);
+        }
+        int32_t packed = ((int32_t)t.pcode[i] << 16) | ((int32_t)t.cls[i] << 24);
+        for (int s = 0; s < 2; ++s) {
+            const int32_t c = t.cidx[2 * (size_t)i + s];
+            ints[s] = c < 0 ? 0 : rowof[c];
+            if (c >= 0) packed |= ((int32_t)t.cls[c] + 1) << (8 * s);
+        }
+        ints[2] = 0;
+        ints[3] = packed;
+    }
+}
+
+void pk_colpart_pack(const pk_tree &t, int precision, unsigned char *dst) {
+    const size_t w = precision == 32 ? 4 : 8;
+    const size_t total = pk_colpart_bytes(t, precision);
+    const size_t npc = 2 * (size_t)t.ncls + 2;
+    std::memset(dst, 0, total);
+    int32_t *hdr = reinterpret_cast<int32_t *>(dst);
+    size_t off = PK_HDR_INTS * 4;
+    hdr[0] = t.n; hdr[1] = t.ncls; hdr[2] = t.nlev; hdr[3] = (int32_t)total; hdr[11] = precision;
+    hdr[4] = (int32_t)off;
+    std::memcpy(dst + off, t.cls_start.data(), (size_t)(t.ncls + 1) * 4);
+    off += align16((size_t)(t.ncls + 1) * 4);
+    hdr[5] = (int32_t)off;
+    std::memcpy(dst + off, t.gstart.data(), t.gstart.size() * 4);
+    off += align16(((size_t)t.ncls * npc + 1) * 4);
     for (int s = 0; s < 2; ++s) {
         hdr[6 + s] = (int32_t)off;
-        for (int32_t row = 0; row < t.n; ++row) {
-            double v = t.bl[2 * (size_t)t.order[row] + s];
-            if (w == 8) reinterpret_cast<double *>(dst + off)[row] = v;
-            else reinterpret_cast<float *>(dst + off)[row] = (float)v;
-        }
+        for (int32_t col = 0; col < t.n; ++col) put_real(dst + off, w, col, t.bl[2 * (size_t)t.colorder[col] + s]);
         off += align16((size_t)t.n * w);
     }
     for (int s = 0; s < 2; ++s) {
         hdr[8 + s] = (int32_t)off;
         int32_t *code = reinterpret_cast<int32_t *>(dst + off);
-        for (int32_t row = 0; row < t.n; ++row) {
-            int32_t c = t.cidx[2 * (size_t)t.order[row] + s];
-            code[row] = c < 0 ? 0 : (((int32_t)t.cls[c] + 1) << 24) | t.rank[c];
+        for (int32_t col = 0; col < t.n; ++col) {
+            const int32_t c = t.cidx[2 * (size_t)t.colorder[col] + s];
+            code[col] = c < 0 ? 0 : (((int32_t)t.cls[c] + 1) << 24) | t.krank[c];
         }
         off += align16((size_t)t.n * 4);
     }
+    hdr[10] = (int32_t)off;
+    int32_t *pc = reinterpret_cast<int32_t *>(dst + off);
+    for (int32_t col = 0; col < t.n; ++col) pc[col] = t.pcode[t.colorder[col]];
 }
 
 // ---------------------------------------------------------------------------------------------------

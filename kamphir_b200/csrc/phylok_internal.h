@@ -34,18 +34,33 @@ struct pk_tree {
     std::vector<int32_t> lvl;       // [ncls * (nlev + 1)]  absolute first kernel row of level L in class c
     std::vector<int64_t> hist;      // [ncls * 2 * (ncls + 1)]  nodes of class c whose slot-s child has class q (0 = tip)
     std::vector<double> heights;    // [n]   ascending node heights, un-normalised
+    // column order: nodes sorted by (class, parent code, post-order).  The parent code of a node is
+    // (class of its parent + 1) * 2 + its slot in the parent (0 for the root).  A C cell (i, j) is read -- by the cell of
+    // the two parents -- only when i and j have the same parent code, so with this order the cells of row i that are
+    // ever read are one contiguous column range, and only that range is stored.
+    std::vector<uint8_t> pcode;     // [n]   post-order index -> parent code, < 2 * ncls + 2
+    std::vector<int32_t> colorder;  // [n]   column -> post-order index
+    std::vector<int32_t> krank;     // [n]   post-order index -> rank within its (class, parent code) group
+    std::vector<int32_t> gstart;    // [ncls * npc + 1]  first column of group (class, parent code); npc = 2 * ncls + 2
 };
 
-// Device block of one tree (16-byte aligned, staged into shared memory with one bulk copy):
-//   int32 hdr[16]   : 0 n | 1 ncls | 2 nlev | 3 block bytes | 4 off cls_start | 5 off lvl | 6 off bl0 | 7 off bl1 |
-//                     8 off code0 | 9 off code1 | 10 ntips | 11 precision | 12,13 bitmask of all-tip-children classes
-//                     (offsets in bytes from block start)
-//   int32 cls_start[ncls + 1]
-//   int32 lvl[ncls][nlev + 1]
-//   real  bl0[n], bl1[n]          (real = double or float; kernel order)
-//   int32 code0[n], code1[n]      (child: (class + 1) << 24 | rank within class;  0 = tip)
-size_t pk_block_bytes(const pk_tree &t, int precision);
-void pk_block_pack(const pk_tree &t, int precision, unsigned char *dst);
+// Device block of one tree: two independently staged parts, both 16-byte aligned.
+//   ROW part (the tree supplies the rows of C), kernel row order = (class, level, post-order):
+//     int32 hdr[16] : 0 n | 1 ncls | 2 nlev | 3 part bytes | 4 off cls_start | 5 off lvl | 6 off row records |
+//                     12,13 bitmask of all-tip-children classes
+//     int32 cls_start[ncls + 1]; int32 lvl[ncls][nlev + 1];
+//     record[n], 32 bytes each: real a0, a1; int32 child-0 row, child-1 row, 0, packed (q0 | q1 << 8 | parent code << 16
+//     | class << 24, q = class + 1 of the child or 0 for a tip); the kernel patches the three ints per pair
+//   COLUMN part (the tree supplies the columns), column order = (class, parent code, post-order):
+//     int32 hdr[16] : 0 n | 1 ncls | 3 part bytes | 4 off cls_start | 5 off gstart | 6 off bl0 | 7 off bl1 | 8 off code0 |
+//                     9 off code1 | 10 off pcode
+//     int32 cls_start[ncls + 1]; int32 gstart[ncls * npc + 1]; real bl0[n], bl1[n];
+//     int32 code0[n], code1[n]   child: (class + 1) << 24 | rank of the child within its (class, parent code) group
+//     int32 pcode[n]
+size_t pk_rowpart_bytes(const pk_tree &t, int precision);
+size_t pk_colpart_bytes(const pk_tree &t, int precision);
+void pk_rowpart_pack(const pk_tree &t, int precision, unsigned char *dst);
+void pk_colpart_pack(const pk_tree &t, int precision, unsigned char *dst);
 
 void pk_set_error(const std::string &msg);
 int pk_fail(int code, const std::string &msg);
