@@ -188,7 +188,8 @@ struct __align__(16) LevelDesc {
 // balanced level barriers -- and a CTA has as many warps as the widest class needs (6 for 500-tip trees), several CTAs
 // (pairs) being resident per SM.
 template <typename T, bool CSMEM, int BOUND>     // BOUND: upper bound of the CTA size (sets the register budget)
-__global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_MINB : 1)) pk_dp_kernel(const DpArgs a) {
+__global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_MINB : BOUND <= 384 ? 2 : 1))
+    pk_dp_kernel(const DpArgs a) {
     const int NT = blockDim.x, NW = NT >> 5;       // any multiple of 32 up to BOUND
     constexpr int U = PK_UNROLL;   // rows in flight per lane
     extern __shared__ __align__(128) unsigned char smem[];
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
                                 const T v = ev[u] * tip2;
-                                if ((rp[u].packed & 0xff0000) == pkey) C[rp[u].st_off + jb] = v + sigma;
+                                if (((rp[u].packed ^ pkey) & 0xff0000) == 0) C[rp[u].st_off + jb] = v + sigma;
                                 part += v;
                             }
                         }
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
                             T x1[1] = {(d0 * d0 + d1 * d1) * neg_inv_tau}, e1[1];
                             pk_gauss<1>(x1, e1, tab_lane, lambda);
                             const T v = e1[0] * tip2;
-                            if ((rp->packed & 0xff0000) == pkey) C[rp->st_off + jb] = v + sigma;
+                            if (((rp->packed ^ pkey) & 0xff0000) == 0) C[rp->st_off + jb] = v + sigma;
                             part += v;
                         }
                     } else {
@@ -384,8 +385,8 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
                                 const RowRec<T> rec = rp[u];
-                                f0[u] = C[(rec.packed & 0xff) == qb0 ? rec.off0 + kb0 : 1];
-                                f1[u] = C[(rec.packed & 0xff00) == qb1 ? rec.off1 + kb1 : 1];
+                                f0[u] = C[((rec.packed ^ qb0) & 0xff) == 0 ? rec.off0 + kb0 : 1];
+                                f1[u] = C[((rec.packed ^ qb1) & 0xff00) == 0 ? rec.off1 + kb1 : 1];
                             }
                         }
                         for (; rr + U <= rend; rr += U, rp += U) {
@@ -396,14 +397,14 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
                                 const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
                                 x[u] = (d0 * d0 + d1 * d1) * neg_inv_tau;
                                 g[u] = f0[u] * f1[u];
-                                so[u] = (rp[u].packed & 0xff0000) == pkey ? rp[u].st_off + jb : -1;
+                                so[u] = ((rp[u].packed ^ pkey) & 0xff0000) == 0 ? rp[u].st_off + jb : -1;
                             }
                             if (rr + 2 * U <= rend) {
 #pragma unroll
                                 for (int u = 0; u < U; ++u) {
                                     const RowRec<T> rec = rp[U + u];
-                                    f0[u] = C[(rec.packed & 0xff) == qb0 ? rec.off0 + kb0 : 1];
-                                    f1[u] = C[(rec.packed & 0xff00) == qb1 ? rec.off1 + kb1 : 1];
+                                    f0[u] = C[((rec.packed ^ qb0) & 0xff) == 0 ? rec.off0 + kb0 : 1];
+                                    f1[u] = C[((rec.packed ^ qb1) & 0xff00) == 0 ? rec.off1 + kb1 : 1];
                                 }
                             }
                             pk_gauss<U>(x, ev, tab_lane, lambda);
@@ -422,8 +423,8 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
                             for (int u = 0; u < U - 1; ++u) {
                                 if (u < rem) {
                                     const RowRec<T> rec = rp[u];
-                                    g0[u] = C[(rec.packed & 0xff) == qb0 ? rec.off0 + kb0 : 1];
-                                    g1[u] = C[(rec.packed & 0xff00) == qb1 ? rec.off1 + kb1 : 1];
+                                    g0[u] = C[((rec.packed ^ qb0) & 0xff) == 0 ? rec.off0 + kb0 : 1];
+                                    g1[u] = C[((rec.packed ^ qb1) & 0xff00) == 0 ? rec.off1 + kb1 : 1];
                                 }
                             }
 #pragma unroll
@@ -433,7 +434,7 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
                                     T x1[1] = {(d0 * d0 + d1 * d1) * neg_inv_tau}, e1[1];
                                     pk_gauss<1>(x1, e1, tab_lane, lambda);
                                     const T v = e1[0] * g0[u] * g1[u];
-                                    if ((rp[u].packed & 0xff0000) == pkey) C[rp[u].st_off + jb] = v + sigma;
+                                    if (((rp[u].packed ^ pkey) & 0xff0000) == 0) C[rp[u].st_off + jb] = v + sigma;
                                     part += v;
                                 }
                             }
@@ -838,11 +839,14 @@ static cudaError_t occupancy_t(int nt, int smem, int *blocks) {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, pk_dp_kernel<T, CSMEM, BOUND>, nt, smem);
 }
 
-// register budgets: <= 224 threads: 72 registers (4 CTAs of 7 warps per SM), <= 256: 80, <= 512: 128, else 64
+// register budgets: <= 224 threads: 72 registers (4 CTAs of 7 warps per SM), <= 256: 80 (3 CTAs), <= 384: 80 (2 CTAs),
+// <= 512: 128, <= 768: 80, else 64 (one CTA per SM)
 #define PK_DISPATCH_NT(FN, TT, CS, ...)                                                         \
     (nt <= 224   ? FN<TT, CS, 224>(__VA_ARGS__)                                                 \
      : nt <= 256 ? FN<TT, CS, 256>(__VA_ARGS__)                                                 \
+     : nt <= 384 ? FN<TT, CS, 384>(__VA_ARGS__)                                                 \
      : nt <= 512 ? FN<TT, CS, 512>(__VA_ARGS__)                                                 \
+     : nt <= 768 ? FN<TT, CS, 768>(__VA_ARGS__)                                                 \
                  : FN<TT, CS, 1024>(__VA_ARGS__))
 #define PK_DISPATCH(FN, ...)                                                                    \
     (prec32 ? (csmem ? PK_DISPATCH_NT(FN, float, true, __VA_ARGS__) : PK_DISPATCH_NT(FN, float, false, __VA_ARGS__)) \
