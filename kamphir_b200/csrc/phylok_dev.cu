@@ -391,13 +391,15 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
                         }
                         for (; rr + U <= rend; rr += U, rp += U) {
                             T x[U], ev[U], g[U];
-                            int so[U];                              // where each row's cell is stored, -1: never read
+                            int so[U];                              // where each row's cell goes if it is ever read
+                            bool st[U];
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
                                 const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
                                 x[u] = (d0 * d0 + d1 * d1) * neg_inv_tau;
                                 g[u] = f0[u] * f1[u];
-                                so[u] = ((rp[u].packed ^ pkey) & 0xff0000) == 0 ? rp[u].st_off + jb : -1;
+                                st[u] = ((rp[u].packed ^ pkey) & 0xff0000) == 0;
+                                so[u] = rp[u].st_off + jb;
                             }
                             if (rr + 2 * U <= rend) {
 #pragma unroll
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
                                 const T v = ev[u] * g[u];
-                                if (so[u] >= 0) C[so[u]] = v + sigma;
+                                if (st[u]) C[so[u]] = v + sigma;
                                 part += v;
                             }
                         }
