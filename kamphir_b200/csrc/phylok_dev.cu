@@ -7,15 +7,16 @@
 //          = sigma + C(ci_s, cj_s)   otherwise
 //   K      = sum of C over production-matched internal-node pairs                      (phyloK2.py:203-204)
 //
-// One CTA evaluates one tree pair (persistent CTAs pull pairs from an atomic work counter).  Both trees' packed
-// node blocks are staged into shared memory with one TMA bulk copy each (cp.async.bulk + mbarrier).  Nodes are
-// stored in "kernel order" (class, level, post-order), so the matched cells of a pair form one dense
-// cntA[c] x cntB[c] rectangle per production class c and C is stored compactly as those rectangles (M cells, not
-// n1*n2).  The tree with fewer levels supplies the rows; level L of the wavefront is then a contiguous row range
-// of each rectangle, evaluated by all warps (a lane owns a column and keeps that node's data in registers while it
-// walks the rows), followed by one __syncthreads.  Child cells live in strictly lower rows, so they are final.
-// Small pairs keep C in shared memory; large pairs keep it in a per-CTA slab in HBM (L2-resident when the slabs of
-// all resident CTAs fit the 126 MB L2): coalesced row writes, predicated child-cell gathers.
+// One CTA evaluates one tree pair (persistent CTAs pull pairs from an atomic work counter).  The row tree's ROW part and
+// the column tree's COLUMN part are staged into shared memory with one TMA bulk copy each (cp.async.bulk + mbarrier).
+// Rows are sorted by (class, level, post-order), columns by (class, parent code, post-order): the matched cells of a
+// pair form one dense cntA[c] x cntB[c] rectangle per production class c, level L of the wavefront is a contiguous row
+// range of each rectangle, and the cells of a row that are ever read again (same parent code) are one contiguous
+// column group -- only that group is stored (R ~ 0.39 M cells).  Thread t owns column t of every rectangle
+// (column-stationary), keeps that node's data in registers while it walks the rows of a (level, class) rectangle four
+// at a time, and all warps meet at one __syncthreads per level (child cells live in strictly lower levels).
+// Stored cells live in shared memory for tiny pairs, otherwise in a per-CTA slab in HBM that stays mostly L2-resident:
+// coalesced group writes, software-pipelined child-cell gathers.
 // No tensor cores (not a contraction), no CPU fallback.
 #include <cuda_runtime.h>
 
