@@ -221,6 +221,7 @@ def run_ours(args):
                          % (args.gpus, world, args.gpus))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("PK_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     t0 = time.perf_counter()
