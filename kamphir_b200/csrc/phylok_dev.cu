@@ -208,6 +208,11 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
     int *rowoff = reinterpret_cast<int *>(smem + info_at);
     T *C = CSMEM ? reinterpret_cast<T *>(smem + info_at + a.rowinfo_bytes)
                  : reinterpret_cast<T *>(a.scratch) + (size_t)blockIdx.x * (size_t)a.slab_elems;
+    if (!CSMEM) {      // keep the slab base in registers instead of re-deriving it from blockIdx in the inner loops
+        unsigned long long cb = reinterpret_cast<unsigned long long>(C);
+        asm volatile("mov.b64 %0, %0;" : "+l"(cb));
+        C = reinterpret_cast<T *>(cb);
+    }
 
     if (tid == 0) mbar_init(&s_bar, 1);
     if (sizeof(T) == 8)
@@ -217,7 +222,8 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
     const T lambda = (T)a.lambda, sigma = (T)a.sigma, neg_inv_tau = (T)a.neg_inv_tau;
     const T tip2 = (sigma + lambda) * (sigma + lambda);        // both children are tip x tip (phyloK2.py:194-196, twice)
     const double *tab_lane = s_tab + (lane & (PK_EXP_REP - 1));
-    const int jb = tid;                                        // this thread's column within every class rectangle
+    int jb;                                                    // this thread's column within every class rectangle
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(jb));           // (opaque, so it lives in a register and is not re-read)
 
     for (unsigned it_no = 0;; ++it_no) {
         if (tid == 0) s_work[it_no & 1] = (long long)atomicAdd(a.counter, 1ull);
@@ -402,10 +408,11 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
                                 st[u] = ((rp[u].packed ^ pkey) & 0xff0000) == 0;
                                 so[u] = rp[u].st_off + jb;
                             }
-                            if (rr + 2 * U <= rend) {
+                            {   // always prefetch (the last group re-reads itself: no join, no register copies)
+                                const RowRec<T> *np = rr + 2 * U <= rend ? rp + U : rp;
 #pragma unroll
                                 for (int u = 0; u < U; ++u) {
-                                    const RowRec<T> rec = rp[U + u];
+                                    const RowRec<T> rec = np[u];
                                     f0[u] = C[((rec.packed ^ qb0) & 0xff) == 0 ? rec.off0 + kb0 : 1];
                                     f1[u] = C[((rec.packed ^ qb1) & 0xff00) == 0 ? rec.off1 + kb1 : 1];
                                 }
