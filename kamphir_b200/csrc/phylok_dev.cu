@@ -201,18 +201,18 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
     __shared__ __align__(16) LevelDesc s_desc[PK_DESC_MAX];
     __shared__ __align__(16) double s_tab[sizeof(T) == 8 ? PK_EXP_TAB * PK_EXP_REP : 2];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int tid;                                                   // opaque read: lives in a register, never re-read via S2R
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const int lane = tid & 31, warp = tid >> 5;
     unsigned char *sA = smem;                                  // ROW part of the row tree (its records are patched in place)
     unsigned char *sB = smem + a.tree_region;                  // COLUMN part of the column tree
     const size_t info_at = (size_t)a.tree_region + a.col_region;
     int *rowoff = reinterpret_cast<int *>(smem + info_at);
-    T *C = CSMEM ? reinterpret_cast<T *>(smem + info_at + a.rowinfo_bytes)
-                 : reinterpret_cast<T *>(a.scratch) + (size_t)blockIdx.x * (size_t)a.slab_elems;
-    if (!CSMEM) {      // keep the slab base in registers instead of re-deriving it from blockIdx in the inner loops
-        unsigned long long cb = reinterpret_cast<unsigned long long>(C);
-        asm volatile("mov.b64 %0, %0;" : "+l"(cb));
-        C = reinterpret_cast<T *>(cb);
-    }
+    // slab offset through an opaque move: it then lives in registers instead of being re-derived from blockIdx inside the
+    // inner loops, while the pointer keeps its global address space (LDG/STG, not generic LD/ST)
+    unsigned long long slab_off = (unsigned long long)blockIdx.x * (unsigned long long)a.slab_elems;
+    asm volatile("mov.b64 %0, %0;" : "+l"(slab_off));
+    T *C = CSMEM ? reinterpret_cast<T *>(smem + info_at + a.rowinfo_bytes) : reinterpret_cast<T *>(a.scratch) + slab_off;
 
     if (tid == 0) mbar_init(&s_bar, 1);
     if (sizeof(T) == 8)
@@ -222,8 +222,7 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
     const T lambda = (T)a.lambda, sigma = (T)a.sigma, neg_inv_tau = (T)a.neg_inv_tau;
     const T tip2 = (sigma + lambda) * (sigma + lambda);        // both children are tip x tip (phyloK2.py:194-196, twice)
     const double *tab_lane = s_tab + (lane & (PK_EXP_REP - 1));
-    int jb;                                                    // this thread's column within every class rectangle
-    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(jb));           // (opaque, so it lives in a register and is not re-read)
+    const int jb = tid;                                        // this thread's column within every class rectangle
 
     for (unsigned it_no = 0;; ++it_no) {
         if (tid == 0) s_work[it_no & 1] = (long long)atomicAdd(a.counter, 1ull);
