@@ -222,7 +222,6 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
     const T lambda = (T)a.lambda, sigma = (T)a.sigma, neg_inv_tau = (T)a.neg_inv_tau;
     const T tip2 = (sigma + lambda) * (sigma + lambda);        // both children are tip x tip (phyloK2.py:194-196, twice)
     const double *tab_lane = s_tab + (lane & (PK_EXP_REP - 1));
-    const int jb = tid;                                        // this thread's column within every class rectangle
 
     for (unsigned it_no = 0;; ++it_no) {
         if (tid == 0) s_work[it_no & 1] = (long long)atomicAdd(a.counter, 1ull);
@@ -348,7 +347,9 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
                 const LevelDesc d = s_desc[e];
                 if (d.rows <= 0) continue;             // uniform
                 const int wB = d.wB;
-                if (jb < wB) {
+                // thread t owns column t; a rectangle wider than the CTA (rare: the CTA is sized for the bulk of the
+                // trees, not the widest) is finished by the first threads taking a second column
+                for (int jb = tid; jb < wB; jb += NT) {
                     const int col = d.colbase + jb;
                     const T b0 = b0p[col], b1 = b1p[col];
                     const int pkey = pcB[col] << 16;              // this column's parent code, aligned with rec.packed
@@ -517,6 +518,7 @@ struct pk_forest {
     std::vector<int32_t> max_cnt;   // per class, max node count over the trees
     std::vector<int32_t> gcnt;      // [n][ncls * npc] nodes per (class, parent code) group
     std::vector<int32_t> max_gcnt;  // [ncls * npc] max over the trees
+    std::vector<int32_t> tree_w;    // [n] widest class of each tree
     std::vector<int32_t> cnt;       // [n][ncls]
     std::vector<int64_t> hist;      // [n][ncls*2*(ncls+1)]
     std::vector<int32_t> nint;      // [n]
@@ -735,6 +737,7 @@ extern "C" int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_
     f->max_gcnt.assign((size_t)ncls * npc, 0);
     f->hist.resize((size_t)n * ncls * 2 * (ncls + 1));
     f->nint.resize(n);
+    f->tree_w.assign(n, 1);
     const size_t meta_bytes = sizeof(int4) * 2 * (size_t)n;
     rc = ensure_pinned(ctx, total + meta_bytes);
     if (rc) {
@@ -759,6 +762,7 @@ extern "C" int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_
             int cnt = t.cls_start[c + 1] - t.cls_start[c];
             f->cnt[(size_t)i * ncls + c] = cnt;
             f->max_cnt[c] = std::max(f->max_cnt[c], cnt);
+            f->tree_w[i] = std::max(f->tree_w[i], cnt);
         }
         for (int g = 0; g < ncls * npc; ++g) {
             const int cnt = t.gstart[g + 1] - t.gstart[g];
@@ -913,14 +917,20 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
     args.rowinfo_bytes = rowinfo;
 
     // one thread per column of the widest class rectangle (column-stationary mapping)
+    // CTA size: one thread per column for ~97 % of the trees (rounded up to a warp); the few wider rectangles are
+    // finished by the first threads taking a second column, instead of every CTA carrying a mostly idle extra warp
     int max_w = 1;
     for (int c = 0; c < fa->ncls; ++c) max_w = std::max(max_w, std::max(fa->max_cnt[c], fb->max_cnt[c]));
-    if (max_w > 1024)
-        return pk_fail(PK_ERR_INVALID, "a production class has " + std::to_string(max_w) +
-                                           " nodes; this build maps one thread per column and supports up to 1024 "
-                                           "(about 3000 tips)");
-    int nt = std::max(64, (max_w + 31) & ~31);
-    if (ctx->cfg_threads && ctx->cfg_threads >= max_w) nt = ctx->cfg_threads;
+    int typ_w;
+    {
+        std::vector<int32_t> ws(fa->tree_w);
+        if (fb != fa) ws.insert(ws.end(), fb->tree_w.begin(), fb->tree_w.end());
+        const size_t k = (size_t)std::min<double>((double)ws.size() - 1, std::floor(0.97 * (double)ws.size()));
+        std::nth_element(ws.begin(), ws.begin() + k, ws.end());
+        typ_w = ws[k];
+    }
+    int nt = std::min(1024, std::max(64, (typ_w + 31) & ~31));
+    if (ctx->cfg_threads) nt = ctx->cfg_threads;
 
     // C in shared memory only when that costs no resident CTAs: with C in a global slab the CTAs of small pairs stay
     // L2-resident anyway and more pairs per SM hide the level barriers better (measured: profiles/r01_summary.md)
