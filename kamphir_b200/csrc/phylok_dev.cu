@@ -60,7 +60,9 @@ struct DpArgs {
     int tree_region;                // shared-memory bytes reserved for the staged ROW part
     int col_region;                 // ... and for the staged COLUMN part
     int rowinfo_bytes;              // row offsets
-    double exp_tab[64];             // lambda * 2^(j/64), j = 0..63 (fp64 Gaussian)
+    double bscale;                  // fp64: sqrt(64 / (ln2 tau)), applied to the staged branch lengths
+    int clamp_hi;                   // fp64 Gaussian: clamp of the exponent's high word
+    unsigned long long exp_tab[64]; // fp64 Gaussian: bits of lambda * 2^(j/64) with the high word biased by -(j << 14)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -95,53 +97,60 @@ __device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// lambda * exp(x) for x <= 0, U independent values at a time
+// lambda * exp(-d^2 / tau), U independent values at a time
 // ---------------------------------------------------------------------------------------------------
-// fp64: x = (k/64) ln2 + r, |r| <= ln2/128; lambda*exp(x) = tab[k & 63] * 2^(k >> 6) * p(r) with tab[j] = lambda * 2^(j/64)
-// (filled by the host in fp64) and p the degree-5 Taylor polynomial (remainder r^6/720 < 3.5e-17; measured max relative
-// error 4e-16).  10 fp64-pipe instructions instead of the ~17 of the generic exp(); below x = -700 the result is
-// ~2^-1022 (true value < 1e-304).  The table is replicated 16x in shared memory (entry j of lane l at word
-// (16 j + (l & 15))): a 64-bit LDS is served per half-warp, so every lookup is conflict-free (2 wavefronts instead of
-// ~4.5 measured with a single copy).  The U chains are written stage by stage so the scheduler interleaves them.
+// fp64: the branch lengths are pre-scaled by sqrt(64 / (ln2 tau)) when a pair is staged, so the squared distance E of two
+// scaled length pairs is the exponent in units of 1/64 octave: lambda * exp(-d^2/tau) = lambda * 2^(-E/64).
+//   t = MAGIC - E (MAGIC = 1.5 * 2^52)  ->  low word of t = k = -round(E);  r = E - round(E), |r| <= 1/2
+//   lambda * 2^(-E/64) = [lambda * 2^(j/64)] * 2^e * 2^(-r/64),   j = k & 63, e = k >> 6
+// The bracket comes from a 64-entry table (filled by the host in fp64), 2^(-r/64) from a degree-4 near-minimax
+// polynomial (max relative error 5e-15, checked on the host over 4e6 arguments), and 2^e is one integer add on the
+// table value's high word: the table stores hi - (j << 14), so hi + (k << 14) adds e << 20.  8 fp64-pipe instructions
+// and 5 integer ones.  E is clamped (one unsigned min on its high word) so that the result stays a normal number
+// (~1e-307 instead of 0 beyond exp(-700)).  The table is replicated 16x in shared memory (entry j of lane l at word
+// 16 j + (l & 15)): a 64-bit LDS is served per half-warp, so every lookup is conflict-free.  The U chains are written
+// stage by stage so the scheduler interleaves them.
 #define PK_EXP_TAB 64
 #define PK_EXP_REP 16
+__constant__ double pk_poly[4] = {-0x1.62e42fefa2417p-7, 0x1.ebfbdff82bb76p-15, -0x1.c6b0b9214b9aep-23,
+                                  0x1.3b2acb2c36b23p-31};   // 2^(-r/64) = 1 + r (c1 + c2 r + c3 r^2 + c4 r^3)
+template <typename T>
+struct GaussK {
+    uint32_t tab_addr;   // shared-memory address of this lane's copy of table entry 0
+    int clamp_hi;        // high word of the largest E that keeps the result normal
+    T lambda, neg_inv_tau;
+};
 template <int U>
-__device__ __forceinline__ void pk_gauss(const double (&x)[U], double (&out)[U], const double *tab_lane, double /*lambda*/) {
-    double t[U], r[U], q[U];
-    int k[U];
+__device__ __forceinline__ void pk_gauss(const double (&E)[U], double (&out)[U], const GaussK<double> &gk) {
+    double Ec[U], t[U], r[U], q[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) t[u] = fma(x[u], 9.23324826168936567683e+01 /* 64/ln2 */, 6755399441055744.0);
+    for (int u = 0; u < U; ++u)
+        Ec[u] = __hiloint2double((int)min((unsigned)__double2hiint(E[u]), (unsigned)gk.clamp_hi), __double2loint(E[u]));
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        k[u] = __double2loint(t[u]);
-        t[u] -= 6755399441055744.0;
-    }
+    for (int u = 0; u < U; ++u) t[u] = 6755399441055744.0 - Ec[u];
 #pragma unroll
-    for (int u = 0; u < U; ++u) r[u] = fma(t[u], -0x1.62e42fee00000p-7 /* (ln2/64) high 32 bits: exact product */, x[u]);
+    for (int u = 0; u < U; ++u) r[u] = (t[u] - 6755399441055744.0) + Ec[u];
 #pragma unroll
-    for (int u = 0; u < U; ++u) r[u] = fma(t[u], -0x1.a39ef35793c76p-39 /* (ln2/64) low part */, r[u]);
+    for (int u = 0; u < U; ++u) q[u] = fma(pk_poly[3], r[u], pk_poly[2]);
 #pragma unroll
-    for (int u = 0; u < U; ++u) q[u] = fma(r[u], 8.3333333333333332e-03, 4.1666666666666664e-02);
+    for (int u = 0; u < U; ++u) q[u] = fma(q[u], r[u], pk_poly[1]);
 #pragma unroll
-    for (int u = 0; u < U; ++u) q[u] = fma(q[u], r[u], 1.6666666666666666e-01);
-#pragma unroll
-    for (int u = 0; u < U; ++u) q[u] = fma(q[u], r[u], 0.5);
-#pragma unroll
-    for (int u = 0; u < U; ++u) q[u] = fma(q[u], r[u], 1.0);
+    for (int u = 0; u < U; ++u) q[u] = fma(q[u], r[u], pk_poly[0]);
 #pragma unroll
     for (int u = 0; u < U; ++u) q[u] = fma(q[u], r[u], 1.0);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        // x < -700 (hi word of x, as unsigned, beyond that of -700.0): pin k so the scale below stays a valid exponent
-        const int kk = (unsigned)__double2hiint(x[u]) >= 0xC085E000u ? -1022 * 64 : k[u];
-        const double p2 = __hiloint2double(__double2hiint(q[u]) + ((kk >> 6) << 20), __double2loint(q[u]));
-        out[u] = p2 * tab_lane[(kk & (PK_EXP_TAB - 1)) * PK_EXP_REP];
+        const int k = __double2loint(t[u]);
+        unsigned lo;
+        int hi;
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(gk.tab_addr + ((k & (PK_EXP_TAB - 1)) << 7)));
+        out[u] = q[u] * __hiloint2double(hi + (k << 14), (int)lo);
     }
 }
 template <int U>
-__device__ __forceinline__ void pk_gauss(const float (&x)[U], float (&out)[U], const double *, float lambda) {
+__device__ __forceinline__ void pk_gauss(const float (&E)[U], float (&out)[U], const GaussK<float> &gk) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) out[u] = lambda * __expf(x[u]);
+    for (int u = 0; u < U; ++u) out[u] = gk.lambda * __expf(E[u] * gk.neg_inv_tau);
 }
 
 // integer division of small non-negative ints through fp32 (exact while a < 2^22 and the quotient's fractional part
@@ -199,7 +208,7 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
     __shared__ int s_cntB[PK_MAX_CLASSES];
     __shared__ double s_part[32];
     __shared__ __align__(16) LevelDesc s_desc[PK_DESC_MAX];
-    __shared__ __align__(16) double s_tab[sizeof(T) == 8 ? PK_EXP_TAB * PK_EXP_REP : 2];
+    __shared__ __align__(16) unsigned long long s_tab[sizeof(T) == 8 ? PK_EXP_TAB * PK_EXP_REP : 2];
 
     int tid;                                                   // opaque read: lives in a register, never re-read via S2R
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
@@ -219,9 +228,13 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
         for (int i = tid; i < PK_EXP_TAB * PK_EXP_REP; i += NT) s_tab[i] = a.exp_tab[i / PK_EXP_REP];
     __syncthreads();
     uint32_t parity = 0;
-    const T lambda = (T)a.lambda, sigma = (T)a.sigma, neg_inv_tau = (T)a.neg_inv_tau;
+    const T lambda = (T)a.lambda, sigma = (T)a.sigma;
     const T tip2 = (sigma + lambda) * (sigma + lambda);        // both children are tip x tip (phyloK2.py:194-196, twice)
-    const double *tab_lane = s_tab + (lane & (PK_EXP_REP - 1));
+    GaussK<T> gk;
+    gk.tab_addr = smem_u32(s_tab) + (lane & (PK_EXP_REP - 1)) * 8;
+    gk.clamp_hi = a.clamp_hi;
+    gk.lambda = lambda;
+    gk.neg_inv_tau = (T)a.neg_inv_tau;
 
     for (unsigned it_no = 0;; ++it_no) {
         if (tid == 0) s_work[it_no & 1] = (long long)atomicAdd(a.counter, 1ull);
@@ -317,6 +330,18 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
             rec->off0 = o0;
             rec->off1 = o1;
             rec->st_off = rowoff[r] - (gstB[c * npc + p] - clsB[c]);       // + column position in the class = stored cell
+            if (sizeof(T) == 8) {                  // fp64: lengths in units that make the squared distance the exponent
+                rec->a0 *= (T)a.bscale;
+                rec->a1 *= (T)a.bscale;
+            }
+        }
+        if (sizeof(T) == 8) {
+            T *b0w = const_cast<T *>(b0p), *b1w = const_cast<T *>(b1p);
+            const int nB = hB[0];
+            for (int c = tid; c < nB; c += NT) {
+                b0w[c] *= (T)a.bscale;
+                b1w[c] *= (T)a.bscale;
+            }
         }
 
         // ---- wavefront over the row tree's levels, a batch of levels at a time -------------------------
@@ -364,9 +389,9 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
                                 const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
-                                x[u] = (d0 * d0 + d1 * d1) * neg_inv_tau;
+                                x[u] = fma(d1, d1, d0 * d0);
                             }
-                            pk_gauss<U>(x, ev, tab_lane, lambda);
+                            pk_gauss<U>(x, ev, gk);
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
                                 const T v = ev[u] * tip2;
@@ -376,8 +401,8 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
                         }
                         for (; rr < rend; ++rr, ++rp) {
                             const T d0 = rp->a0 - b0, d1 = rp->a1 - b1;
-                            T x1[1] = {(d0 * d0 + d1 * d1) * neg_inv_tau}, e1[1];
-                            pk_gauss<1>(x1, e1, tab_lane, lambda);
+                            T x1[1] = {fma(d1, d1, d0 * d0)}, e1[1];
+                            pk_gauss<1>(x1, e1, gk);
                             const T v = e1[0] * tip2;
                             if (((rp->packed ^ pkey) & 0xff0000) == 0) C[rp->st_off + jb] = v + sigma;
                             part += v;
@@ -403,7 +428,7 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
                                 const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
-                                x[u] = (d0 * d0 + d1 * d1) * neg_inv_tau;
+                                x[u] = fma(d1, d1, d0 * d0);
                                 g[u] = f0[u] * f1[u];
                                 st[u] = ((rp[u].packed ^ pkey) & 0xff0000) == 0;
                                 so[u] = rp[u].st_off + jb;
@@ -417,7 +442,7 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
                                     f1[u] = C[((rec.packed ^ qb1) & 0xff00) == 0 ? rec.off1 + kb1 : 1];
                                 }
                             }
-                            pk_gauss<U>(x, ev, tab_lane, lambda);
+                            pk_gauss<U>(x, ev, gk);
 #pragma unroll
                             for (int u = 0; u < U; ++u) {
                                 const T v = ev[u] * g[u];
@@ -441,8 +466,8 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
                             for (int u = 0; u < U - 1; ++u) {
                                 if (u < rem) {
                                     const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
-                                    T x1[1] = {(d0 * d0 + d1 * d1) * neg_inv_tau}, e1[1];
-                                    pk_gauss<1>(x1, e1, tab_lane, lambda);
+                                    T x1[1] = {fma(d1, d1, d0 * d0)}, e1[1];
+                                    pk_gauss<1>(x1, e1, gk);
                                     const T v = e1[0] * g0[u] * g1[u];
                                     if (((rp[u].packed ^ pkey) & 0xff0000) == 0) C[rp[u].st_off + jb] = v + sigma;
                                     part += v;
@@ -475,6 +500,27 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
             }
         }
         // the next iteration's first __syncthreads orders these reads before the staging buffers are overwritten
+    }
+}
+
+// decayFactor == 0: every C(n1, n2) is exactly 0 (phyloK2.py:184-199 multiplies by it), so K = 0 for every work item
+// (0/0 = NaN where a normalisation by the zero diagonal is requested).  Same work decoding as pk_dp_kernel.
+__global__ void pk_zero_kernel(const DpArgs a) {
+    for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < a.total; w += (long long)gridDim.x * blockDim.x) {
+        if (a.mode == 0) {
+            a.out[w] = 0.0;
+        } else if (a.mode == 1) {
+            const int sh = a.tile_shift;
+            const int2 t = a.tiles[w >> (2 * sh)];
+            const int r = (int)(w & ((1ll << (2 * sh)) - 1));
+            const int ia = (t.x << sh) + (r >> sh), ib = (t.y << sh) + (r & ((1 << sh) - 1));
+            if (ib < ia || ib >= a.n_trees || ia >= a.n_trees) continue;
+            const double k = a.diag ? 0.0 / sqrt(a.diag[ia] * a.diag[ib]) : 0.0;
+            a.out[(long long)ia * a.ld + ib] = k;
+            a.out[(long long)ib * a.ld + ia] = k;
+        } else {
+            a.out[w] = 0.0;
+        }
     }
 }
 
@@ -884,7 +930,32 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
     args.lambda = p->decay;
     args.neg_inv_tau = -1.0 / p->gauss;
     args.sigma = p->sigma;
-    for (int j = 0; j < 64; ++j) args.exp_tab[j] = p->decay * std::exp2((double)j / 64.0);
+    if (p->decay == 0.0) {
+        pk_zero_kernel<<<(int)std::min<long long>((args.total + 255) / 256, 1024), 256, 0, ctx->stream>>>(args);
+        PK_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return PK_OK;
+    }
+    if (!prec32) {
+        // fp64 Gaussian (pk_gauss): table of lambda * 2^(j/64) with the high word biased by -(j << 14), the clamp that
+        // keeps lambda * 2^(-E/64) a normal number, and the length scale that turns d^2/tau into 1/64 octaves
+        if (!(p->gauss > 0.0)) return pk_fail(PK_ERR_INVALID, "gaussFactor must be positive");
+        if (!(p->decay > 0.0) || p->decay < 1e-200 || p->decay > 1e200)
+            return pk_fail(PK_ERR_INVALID, "decayFactor must be in [1e-200, 1e200]");
+        for (int j = 0; j < 64; ++j) {
+            const double t = p->decay * std::exp2((double)j / 64.0);
+            unsigned long long bits;
+            std::memcpy(&bits, &t, 8);
+            const uint32_t hi = (uint32_t)(bits >> 32) - ((uint32_t)j << 14);
+            args.exp_tab[j] = ((unsigned long long)hi << 32) | (bits & 0xffffffffull);
+        }
+        const int emin = 2 - 1023 - (int)std::floor(std::log2(p->decay));
+        const double emax = -64.0 * (double)emin - 1.0;
+        unsigned long long eb;
+        std::memcpy(&eb, &emax, 8);
+        args.clamp_hi = (int)(eb >> 32) - 1;
+        args.bscale = std::sqrt(64.0 / (std::log(2.0) * p->gauss));
+    }
 
     // Upper bound of the stored C cells over all pairs: row i keeps one cell per column of its own (class, parent code)
     // group, so a pair stores sum_g rows_g * cols_g cells; bound the columns by the per-group maximum over both forests.
