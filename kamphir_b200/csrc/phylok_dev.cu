@@ -163,8 +163,8 @@ __device__ __forceinline__ int pk_div(int a, int b) { return __float2int_rz(__fd
 template <typename T>
 struct __align__(16) RowRec {
     T a0, a1;
-    int off0, off1, st_off, packed;
-    char pad[32 - 2 * sizeof(T) - 16];
+    char pad[16 - 2 * sizeof(T)];
+    int off0, off1, st_off, packed;     // bytes 16..31: read as one int4
 };
 template <>
 struct __align__(16) RowRec<double> {
@@ -179,16 +179,158 @@ struct __align__(16) LevelDesc {
     int wB;         // columns = nodes of the column tree in this class
     int colbase;    // first column (kernel order in the column tree)
     int cbase;      // unused (rows carry their own C offsets)
-    int flags;      // bit 8: last rectangle of its level (a barrier follows); bit 9: all-tip-children class
+    int flags;      // bit 8: last rectangle of its level (a barrier follows); bit 9 / 10: slot 0 / 1 always a tip
     int pad0, pad1;
 };
-#define PK_DESC_MAX 192
+#ifndef PK_DESC_MAX
+#define PK_DESC_MAX 48
+#endif
+
+// ---------------------------------------------------------------------------------------------------
+// stored C cells of one pair: a shared-memory array (tiny trees) or this CTA's slab in HBM.  The slab base is an opaque
+// 64-bit value in a vector register pair, so every cell address is one IMAD.WIDE with an immediate 8 (or 4); the accesses
+// are explicit ld.global / st.global (the opaque base would otherwise decay to generic LD/ST).
+// ---------------------------------------------------------------------------------------------------
+template <typename T, bool CSMEM>
+struct Cells {
+    T *sm;
+    unsigned long long base;
+    __device__ __forceinline__ T ld(int idx) const {
+        if (CSMEM) return sm[idx];
+        T v;
+        const unsigned long long addr = base + (unsigned long long)(unsigned)idx * sizeof(T);
+        if (sizeof(T) == 8) asm volatile("ld.global.f64 %0, [%1];" : "=d"(*reinterpret_cast<double *>(&v)) : "l"(addr));
+        else asm volatile("ld.global.f32 %0, [%1];" : "=f"(*reinterpret_cast<float *>(&v)) : "l"(addr));
+        return v;
+    }
+    __device__ __forceinline__ void st(int idx, T v) const {
+        if (CSMEM) {
+            sm[idx] = v;
+            return;
+        }
+        const unsigned long long addr = base + (unsigned long long)(unsigned)idx * sizeof(T);
+        if (sizeof(T) == 8) asm volatile("st.global.f64 [%0], %1;" ::"l"(addr), "d"(*reinterpret_cast<double *>(&v)) : "memory");
+        else asm volatile("st.global.f32 [%0], %1;" ::"l"(addr), "f"(*reinterpret_cast<float *>(&v)) : "memory");
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// one column of one (level, class) rectangle: the thread keeps its column's node in registers and walks the rows U at a
+// time.  G0 / G1: slot 0 / 1 of the rows has internal children somewhere in this class (otherwise that slot is a tip in
+// every row and its factor is a per-column constant: sigma + lambda against a tip, 1 against an internal node).
+//   C(i,j) = lambda * exp(-((a0-b0)^2 + (a1-b1)^2) / tau) * f0 * f1                       (phyloK2.py:184-199)
+// Software pipeline: the second half of the NEXT group's row records (child-row offsets, store offset, class bytes) is
+// read and its child-cell gathers are issued before the Gaussians of the current group, so the L2 / HBM latency of the
+// gathers is covered; the store offset and parent code of a group ride along in registers (each record half is read
+// once).  Returns the column's partial sum of C over the rows.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int4 lds_int4(const int4 *p) {     // always one LDS.128 (never split into scalar loads)
+    int4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
+
+template <typename T, bool CSMEM, bool G0, bool G1, int U>
+__device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0, T b1, int cb0, int cb1, int pkey,
+                                     const Cells<T, CSMEM> &C, const GaussK<T> &gk, T sigma, T tipf) {
+    const int qb0 = (unsigned)cb0 >> 24, kb0 = cb0 & 0xffffff;             // child class + 1 (0 = tip), rank in its group
+    const int qb1 = ((unsigned)cb1 >> 24) << 8, kb1 = cb1 & 0xffffff;      // ... aligned with byte 1 of rec.packed
+    T cf = (T)1;                                                           // factor of the slots that are tips in every row
+    if (!G0) cf = qb0 == 0 ? tipf : (T)1;
+    if (!G1) cf *= qb1 == 0 ? tipf : (T)1;
+    T part = (T)0;
+    T f0[U], f1[U];
+    int so[U], pm[U];
+    int rr = 0;
+    const int4 *ip = reinterpret_cast<const int4 *>(rp);                   // ip[2 r + 1] = {off0, off1, st_off, packed}
+    if (U <= rows) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int4 q = lds_int4(ip + 2 * u + 1);
+            if (G0) f0[u] = C.ld(((q.w ^ qb0) & 0xff) == 0 ? q.x + kb0 : 1);
+            if (G1) f1[u] = C.ld(((q.w ^ qb1) & 0xff00) == 0 ? q.y + kb1 : 1);
+            so[u] = q.z + jb;
+            pm[u] = q.w;
+        }
+    }
+    for (; rr + U <= rows; rr += U, rp += U, ip += 2 * U) {
+        T x[U], ev[U], g[U];
+        int cso[U], cpm[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
+            x[u] = fma(d1, d1, d0 * d0);
+            g[u] = G0 ? (G1 ? f0[u] * f1[u] : f0[u] * cf) : (G1 ? f1[u] * cf : cf);
+            cso[u] = so[u];
+            cpm[u] = pm[u];
+        }
+        if (G0 || G1) {   // always prefetch (the last group re-reads itself: no join, no register copies)
+            const int4 *np = rr + 2 * U <= rows ? ip + 2 * U : ip;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int4 q = lds_int4(np + 2 * u + 1);
+                if (G0) f0[u] = C.ld(((q.w ^ qb0) & 0xff) == 0 ? q.x + kb0 : 1);
+                if (G1) f1[u] = C.ld(((q.w ^ qb1) & 0xff00) == 0 ? q.y + kb1 : 1);
+                so[u] = q.z + jb;
+                pm[u] = q.w;
+            }
+        } else {
+            const int4 *np = rr + 2 * U <= rows ? ip + 2 * U : ip;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int2 q = *reinterpret_cast<const int2 *>(reinterpret_cast<const int *>(np + 2 * u + 1) + 2);
+                so[u] = q.x + jb;
+                pm[u] = q.y;
+            }
+        }
+        pk_gauss<U>(x, ev, gk);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const T v = ev[u] * g[u];
+#ifdef PK_CARRY
+            if (((cpm[u] ^ pkey) & 0xff0000) == 0) C.st(cso[u], v + sigma);
+#else
+            if (((rp[u].packed ^ pkey) & 0xff0000) == 0) C.st(rp[u].st_off + jb, v + sigma);
+#endif
+            part += v;
+        }
+    }
+    // the last 1..U-1 rows: all their gathers first (one exposed round trip, not one per row)
+    const int rem = rows - rr;
+    if (rem > 0) {
+        T g0[U - 1], g1[U - 1];
+#pragma unroll
+        for (int u = 0; u < U - 1; ++u) {
+            if (u < rem) {
+                const int4 q = lds_int4(ip + 2 * u + 1);
+                if (G0) g0[u] = C.ld(((q.w ^ qb0) & 0xff) == 0 ? q.x + kb0 : 1);
+                if (G1) g1[u] = C.ld(((q.w ^ qb1) & 0xff00) == 0 ? q.y + kb1 : 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U - 1; ++u) {
+            if (u < rem) {
+                const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
+                T x1[1] = {fma(d1, d1, d0 * d0)}, e1[1];
+                pk_gauss<1>(x1, e1, gk);
+                const T g = G0 ? (G1 ? g0[u] * g1[u] : g0[u] * cf) : (G1 ? g1[u] * cf : cf);
+                const T v = e1[0] * g;
+                if (((rp[u].packed ^ pkey) & 0xff0000) == 0) C.st(rp[u].st_off + jb, v + sigma);
+                part += v;
+            }
+        }
+    }
+    return part;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // the DP kernel
 // ---------------------------------------------------------------------------------------------------
 #ifndef PK_UNROLL
 #define PK_UNROLL 4
+#endif
+#ifndef PK_U2_BOUND
+#define PK_U2_BOUND 256
 #endif
 #ifndef PK_MINB
 #define PK_MINB 3
@@ -198,10 +340,15 @@ struct __align__(16) LevelDesc {
 // balanced level barriers -- and a CTA has as many warps as the widest class needs (6 for 500-tip trees), several CTAs
 // (pairs) being resident per SM.
 template <typename T, bool CSMEM, int BOUND>     // BOUND: upper bound of the CTA size (sets the register budget)
-__global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_MINB : BOUND <= 384 ? 2 : 1))
+#ifndef PK_MINB192
+#define PK_MINB192 4
+#endif
+__global__ void __launch_bounds__(BOUND, (BOUND <= 192 ? PK_MINB192 : BOUND <= 224 ? 4 : BOUND <= 256 ? PK_MINB : BOUND <= 384 ? 2 : 1))   // 192: 80 registers
     pk_dp_kernel(const DpArgs a) {
     const int NT = blockDim.x, NW = NT >> 5;       // any multiple of 32 up to BOUND
-    constexpr int U = PK_UNROLL;   // rows in flight per lane
+    // rows in flight per lane: 2 where several CTAs share an SM (more, lighter warps hide the latencies better: measured
+    // 445 vs 410 Gcells/s at 500 tips), 4 where one big CTA owns the SM (2000 tips: 417 vs 363)
+    constexpr int U = BOUND <= PK_U2_BOUND ? 2 : PK_UNROLL;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ long long s_work[2];
@@ -217,19 +364,22 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
     unsigned char *sB = smem + a.tree_region;                  // COLUMN part of the column tree
     const size_t info_at = (size_t)a.tree_region + a.col_region;
     int *rowoff = reinterpret_cast<int *>(smem + info_at);
-    // slab offset through an opaque move: it then lives in registers instead of being re-derived from blockIdx inside the
-    // inner loops, while the pointer keeps its global address space (LDG/STG, not generic LD/ST)
-    unsigned long long slab_off = (unsigned long long)blockIdx.x * (unsigned long long)a.slab_elems;
-    asm volatile("mov.b64 %0, %0;" : "+l"(slab_off));
-    T *C = CSMEM ? reinterpret_cast<T *>(smem + info_at + a.rowinfo_bytes) : reinterpret_cast<T *>(a.scratch) + slab_off;
-
+    const unsigned long long slab_off = (unsigned long long)blockIdx.x * (unsigned long long)a.slab_elems;
+    Cells<T, CSMEM> cells;
+    cells.sm = reinterpret_cast<T *>(smem + info_at + a.rowinfo_bytes);
+    cells.base = (unsigned long long)(reinterpret_cast<T *>(a.scratch) + slab_off);
     if (tid == 0) mbar_init(&s_bar, 1);
     if (sizeof(T) == 8)
         for (int i = tid; i < PK_EXP_TAB * PK_EXP_REP; i += NT) s_tab[i] = a.exp_tab[i / PK_EXP_REP];
+    if (tid < 32) s_part[tid] = 0.0;
     __syncthreads();
+    // the slab base plus a zero read from a lane-dependent shared-memory address: ptxas cannot prove the sum uniform, so it stays in a vector
+    // register pair and a cell address is one IMAD.WIDE idx, 8, base (a uniform base needs the 8 in a register: one
+    // extra MOV per access)
+    cells.base += (unsigned long long)*reinterpret_cast<volatile long long *>(&s_part[lane]);
     uint32_t parity = 0;
     const T lambda = (T)a.lambda, sigma = (T)a.sigma;
-    const T tip2 = (sigma + lambda) * (sigma + lambda);        // both children are tip x tip (phyloK2.py:194-196, twice)
+    const T tipf = sigma + lambda;                             // child factor tip x tip (phyloK2.py:194-196)
     GaussK<T> gk;
     gk.tab_addr = smem_u32(s_tab) + (lane & (PK_EXP_REP - 1)) * 8;
     gk.clamp_hi = a.clamp_hi;
@@ -279,7 +429,9 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
         const int *hA = reinterpret_cast<const int *>(sA);
         const int *hB = reinterpret_cast<const int *>(sB);
         const int nA = hA[0], ncls = hA[1], nlevA = hA[2], npc = 2 * ncls + 2;
-        const unsigned long long tipmask = (unsigned)hA[12] | ((unsigned long long)(unsigned)hA[13] << 32);
+        // classes whose rows all have a tip in slot 0 / slot 1 (those slots need no child-cell gathers)
+        const unsigned long long tip0mask = (unsigned)hA[7] | ((unsigned long long)(unsigned)hA[8] << 32);
+        const unsigned long long tip1mask = (unsigned)hA[9] | ((unsigned long long)(unsigned)hA[10] << 32);
         const int *lvlA = reinterpret_cast<const int *>(sA + hA[5]);
         RowRec<T> *rowrec = reinterpret_cast<RowRec<T> *>(sA + hA[6]);
         const int *clsB = reinterpret_cast<const int *>(sB + hB[4]);
@@ -296,8 +448,8 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
         //      contiguous column group with its own parent code: R cells per pair instead of M.
         if (tid < ncls) s_cntB[tid] = clsB[tid + 1] - clsB[tid];
         if (tid == 0) {
-            C[0] = sigma + lambda;   // tip x tip child factor (phyloK2.py:194-196)
-            C[1] = (T)1;             // factor of a child slot whose productions differ (phyloK2.py:191-192)
+            cells.st(0, tipf);       // tip x tip child factor (phyloK2.py:194-196)
+            cells.st(1, (T)1);       // factor of a child slot whose productions differ (phyloK2.py:191-192)
         }
         // row offsets: exclusive scan of the stored row lengths, by warp 0 (32 rows per step, running carry)
         if (warp == 0) {
@@ -359,7 +511,7 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
                     d.r0 = r0; d.rows = 0; d.wB = wB; d.colbase = clsB[c]; d.cbase = 0; d.flags = 0; d.pad0 = d.pad1 = 0;
                     if (rows > 0 && wB > 0) {
                         d.rows = rows;
-                        d.flags = ((tipmask >> c) & 1ull) ? 512 : 0;
+                        d.flags = (((tip0mask >> c) & 1ull) ? 512 : 0) | (((tip1mask >> c) & 1ull) ? 1024 : 0);
                         last = c;
                     }
                     dst[c] = d;
@@ -378,102 +530,24 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 224 ? 4 : BOUND <= 256 ? PK_M
                     const int col = d.colbase + jb;
                     const T b0 = b0p[col], b1 = b1p[col];
                     const int pkey = pcB[col] << 16;              // this column's parent code, aligned with rec.packed
-                    const int rend = d.r0 + d.rows;
                     const RowRec<T> *rp = rowrec + d.r0;
-                    T part = (T)0;
-                    int rr = d.r0;
-                    if (d.flags & 512) {
-                        // class whose nodes have two tip children: no child cells, f0*f1 = (sigma+lambda)^2
-                        for (; rr + U <= rend; rr += U, rp += U) {
-                            T x[U], ev[U];
-#pragma unroll
-                            for (int u = 0; u < U; ++u) {
-                                const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
-                                x[u] = fma(d1, d1, d0 * d0);
-                            }
-                            pk_gauss<U>(x, ev, gk);
-#pragma unroll
-                            for (int u = 0; u < U; ++u) {
-                                const T v = ev[u] * tip2;
-                                if (((rp[u].packed ^ pkey) & 0xff0000) == 0) C[rp[u].st_off + jb] = v + sigma;
-                                part += v;
-                            }
-                        }
-                        for (; rr < rend; ++rr, ++rp) {
-                            const T d0 = rp->a0 - b0, d1 = rp->a1 - b1;
-                            T x1[1] = {fma(d1, d1, d0 * d0)}, e1[1];
-                            pk_gauss<1>(x1, e1, gk);
-                            const T v = e1[0] * tip2;
-                            if (((rp->packed ^ pkey) & 0xff0000) == 0) C[rp->st_off + jb] = v + sigma;
-                            part += v;
-                        }
-                    } else {
-                        const int cb0 = codeB0[col], cb1 = codeB1[col];
-                        const int qb0 = cb0 >> 24, kb0 = cb0 & 0xffffff, qb1 = (cb1 >> 24) << 8, kb1 = cb1 & 0xffffff;
-                        // software pipeline: the child-cell gathers of the NEXT group of U rows are issued before the
-                        // Gaussians of the current group, so their (L2/HBM) latency is covered
-                        T f0[U], f1[U];
-                        if (rr + U <= rend) {
-#pragma unroll
-                            for (int u = 0; u < U; ++u) {
-                                const RowRec<T> rec = rp[u];
-                                f0[u] = C[((rec.packed ^ qb0) & 0xff) == 0 ? rec.off0 + kb0 : 1];
-                                f1[u] = C[((rec.packed ^ qb1) & 0xff00) == 0 ? rec.off1 + kb1 : 1];
-                            }
-                        }
-                        for (; rr + U <= rend; rr += U, rp += U) {
-                            T x[U], ev[U], g[U];
-                            int so[U];                              // where each row's cell goes if it is ever read
-                            bool st[U];
-#pragma unroll
-                            for (int u = 0; u < U; ++u) {
-                                const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
-                                x[u] = fma(d1, d1, d0 * d0);
-                                g[u] = f0[u] * f1[u];
-                                st[u] = ((rp[u].packed ^ pkey) & 0xff0000) == 0;
-                                so[u] = rp[u].st_off + jb;
-                            }
-                            {   // always prefetch (the last group re-reads itself: no join, no register copies)
-                                const RowRec<T> *np = rr + 2 * U <= rend ? rp + U : rp;
-#pragma unroll
-                                for (int u = 0; u < U; ++u) {
-                                    const RowRec<T> rec = np[u];
-                                    f0[u] = C[((rec.packed ^ qb0) & 0xff) == 0 ? rec.off0 + kb0 : 1];
-                                    f1[u] = C[((rec.packed ^ qb1) & 0xff00) == 0 ? rec.off1 + kb1 : 1];
-                                }
-                            }
-                            pk_gauss<U>(x, ev, gk);
-#pragma unroll
-                            for (int u = 0; u < U; ++u) {
-                                const T v = ev[u] * g[u];
-                                if (st[u]) C[so[u]] = v + sigma;
-                                part += v;
-                            }
-                        }
-                        // the last 1..U-1 rows: all their gathers first (one exposed round trip, not one per row)
-                        const int rem = rend - rr;
-                        if (rem > 0) {
-                            T g0[U - 1], g1[U - 1];
-#pragma unroll
-                            for (int u = 0; u < U - 1; ++u) {
-                                if (u < rem) {
-                                    const RowRec<T> rec = rp[u];
-                                    g0[u] = C[((rec.packed ^ qb0) & 0xff) == 0 ? rec.off0 + kb0 : 1];
-                                    g1[u] = C[((rec.packed ^ qb1) & 0xff00) == 0 ? rec.off1 + kb1 : 1];
-                                }
-                            }
-#pragma unroll
-                            for (int u = 0; u < U - 1; ++u) {
-                                if (u < rem) {
-                                    const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
-                                    T x1[1] = {fma(d1, d1, d0 * d0)}, e1[1];
-                                    pk_gauss<1>(x1, e1, gk);
-                                    const T v = e1[0] * g0[u] * g1[u];
-                                    if (((rp[u].packed ^ pkey) & 0xff0000) == 0) C[rp[u].st_off + jb] = v + sigma;
-                                    part += v;
-                                }
-                            }
-                        }
+                    T part;
+                    switch (d.flags & (512 | 1024)) {             // bit 9 / 10: slot 0 / 1 is a tip in every row of the class
+                    case 512 | 1024:
+                        part = pk_rect<T, CSMEM, false, false, U>(rp, d.rows, jb, b0, b1, codeB0[col], codeB1[col], pkey, cells,
+                                                                  gk, sigma, tipf);
+                        break;
+                    case 512:
+                        part = pk_rect<T, CSMEM, false, true, U>(rp, d.rows, jb, b0, b1, codeB0[col], codeB1[col], pkey, cells,
+                                                                 gk, sigma, tipf);
+                        break;
+                    case 1024:
+                        part = pk_rect<T, CSMEM, true, false, U>(rp, d.rows, jb, b0, b1, codeB0[col], codeB1[col], pkey, cells,
+                                                                 gk, sigma, tipf);
+                        break;
+                    default:
+                        part = pk_rect<T, CSMEM, true, true, U>(rp, d.rows, jb, b0, b1, codeB0[col], codeB1[col], pkey, cells,
+                                                                gk, sigma, tipf);
                     }
                     acc += (double)part;
                 }
@@ -901,7 +975,8 @@ static cudaError_t occupancy_t(int nt, int smem, int *blocks) {
 // register budgets: <= 224 threads: 72 registers (4 CTAs of 7 warps per SM), <= 256: 80 (3 CTAs), <= 384: 80 (2 CTAs),
 // <= 512: 128, <= 768: 80, else 64 (one CTA per SM)
 #define PK_DISPATCH_NT(FN, TT, CS, ...)                                                         \
-    (nt <= 224   ? FN<TT, CS, 224>(__VA_ARGS__)                                                 \
+    (nt <= 192   ? FN<TT, CS, 192>(__VA_ARGS__)                                                 \
+     : nt <= 224 ? FN<TT, CS, 224>(__VA_ARGS__)                                                 \
      : nt <= 256 ? FN<TT, CS, 256>(__VA_ARGS__)                                                 \
      : nt <= 384 ? FN<TT, CS, 384>(__VA_ARGS__)                                                 \
      : nt <= 512 ? FN<TT, CS, 512>(__VA_ARGS__)                                                 \

@@ -441,26 +441,44 @@ int pk_tree_finish(pk_tree &t) {
         t.order[row] = i;
         t.rank[i] = row - t.cls_start[t.cls[i]];
     }
-    // parent codes and the column order (class, parent code, post-order)
+    // parent codes and the column order (class, parent code, ancestor path, post-order)
     const int npc = 2 * ncls + 2;
     t.pcode.assign(n, 0);
+    std::vector<int32_t> parent(n, -1);
     for (int32_t i = 0; i < n; ++i)
         for (int s = 0; s < 2; ++s) {
             int32_t c = t.cidx[2 * (size_t)i + s];
-            if (c >= 0) t.pcode[c] = (uint8_t)((t.cls[i] + 1) * 2 + s);
+            if (c >= 0) {
+                t.pcode[c] = (uint8_t)((t.cls[i] + 1) * 2 + s);
+                parent[c] = i;
+            }
         }
     t.gstart.assign((size_t)ncls * npc + 1, 0);
     for (int32_t i = 0; i < n; ++i) t.gstart[(size_t)t.cls[i] * npc + t.pcode[i] + 1]++;
     for (size_t k = 1; k < t.gstart.size(); ++k) t.gstart[k] += t.gstart[k - 1];
+    // Within a (class, parent code) group the columns are ordered by the parent codes of their ancestors (parent first),
+    // i.e. like their parents are ordered among the columns of the parents' class.  The child cells that 32 consecutive
+    // columns gather from one stored row are then (almost) consecutive too: 3.6 sectors per gather instead of 6.8 at
+    // 500 tips.  Five ancestors are enough (measured: 3.9 sectors with 4, 3.6 with 6 or 40).
     t.colorder.assign(n, 0);
     t.krank.assign(n, 0);
     {
-        std::vector<int32_t> fill(t.gstart.begin(), t.gstart.end() - 1);
+        constexpr int kPath = 5;
+        std::vector<std::pair<uint64_t, int32_t>> keys(n);
         for (int32_t i = 0; i < n; ++i) {
-            const size_t g = (size_t)t.cls[i] * npc + t.pcode[i];
-            const int32_t col = fill[g]++;
+            uint64_t k = t.cls[i];
+            int32_t v = i;
+            for (int d = 0; d < kPath; ++d) {
+                k = (k << 8) | (v >= 0 ? t.pcode[v] : 0);
+                if (v >= 0) v = parent[v];
+            }
+            keys[i] = {k, i};
+        }
+        std::sort(keys.begin(), keys.end());
+        for (int32_t col = 0; col < n; ++col) {
+            const int32_t i = keys[col].second;
             t.colorder[col] = i;
-            t.krank[i] = col - t.gstart[g];
+            t.krank[i] = col - t.gstart[(size_t)t.cls[i] * npc + t.pcode[i]];
         }
     }
     t.hist.assign((size_t)ncls * 2 * (ncls + 1), 0);
@@ -508,18 +526,16 @@ void pk_rowpart_pack(const pk_tree &t, int precision, unsigned char *dst) {
     int32_t *hdr = reinterpret_cast<int32_t *>(dst);
     size_t off = PK_HDR_INTS * 4;
     hdr[0] = t.n; hdr[1] = t.ncls; hdr[2] = t.nlev; hdr[3] = (int32_t)total; hdr[11] = precision;
-    {   // classes whose nodes all have two tip children (their cells need no child-cell gathers); bit c of hdr[12..13]
+    for (int sl = 0; sl < 2; ++sl) {   // classes whose nodes all have a tip in slot sl (no child-cell gathers for that slot)
         uint64_t mask = 0;
         for (int c = 0; c < t.ncls; ++c) {
             bool all = true;
-            for (int32_t row = t.cls_start[c]; row < t.cls_start[c + 1] && all; ++row) {
-                const int32_t i = t.order[row];
-                all = t.cidx[2 * (size_t)i] < 0 && t.cidx[2 * (size_t)i + 1] < 0;
-            }
+            for (int32_t row = t.cls_start[c]; row < t.cls_start[c + 1] && all; ++row)
+                all = t.cidx[2 * (size_t)t.order[row] + sl] < 0;
             if (all) mask |= (uint64_t)1 << c;
         }
-        hdr[12] = (int32_t)(mask & 0xffffffffu);
-        hdr[13] = (int32_t)(mask >> 32);
+        hdr[7 + 2 * sl] = (int32_t)(mask & 0xffffffffu);
+        hdr[8 + 2 * sl] = (int32_t)(mask >> 32);
     }
     hdr[4] = (int32_t)off;
     std::memcpy(dst + off, t.cls_start.data(), (size_t)(t.ncls + 1) * 4);
@@ -540,7 +556,7 @@ void pk_rowpart_pack(const pk_tree &t, int precision, unsigned char *dst) {
         if (precision == 32) {
             reinterpret_cast<float *>(rec)[0] = (float)t.bl[2 * (size_t)i];
             reinterpret_cast<float *>(rec)[1] = (float)t.bl[2 * (size_t)i + 1];
-            ints = reinterpret_cast<int32_t *>(rec + 8);
+            ints = reinterpret_cast<int32_t *>(rec + 16);
         } else {
             reinterpret_cast<double *>(rec)[0] = t.bl[2 * (size_t)i];
             reinterpret_cast<double *>(rec)[1] = t.bl[2 * (size_t)i + 1];

@@ -34,7 +34,7 @@ struct pk_tree {
     std::vector<int32_t> lvl;       // [ncls * (nlev + 1)]  absolute first kernel row of level L in class c
     std::vector<int64_t> hist;      // [ncls * 2 * (ncls + 1)]  nodes of class c whose slot-s child has class q (0 = tip)
     std::vector<double> heights;    // [n]   ascending node heights, un-normalised
-    // column order: nodes sorted by (class, parent code, post-order).  The parent code of a node is
+    // column order: nodes sorted by (class, parent code, parent codes of the next ancestors, post-order).  The parent code of a node is
     // (class of its parent + 1) * 2 + its slot in the parent (0 for the root).  A C cell (i, j) is read -- by the cell of
     // the two parents -- only when i and j have the same parent code, so with this order the cells of row i that are
     // ever read are one contiguous column range, and only that range is stored.
@@ -47,7 +47,7 @@ struct pk_tree {
 // Device block of one tree: two independently staged parts, both 16-byte aligned.
 //   ROW part (the tree supplies the rows of C), kernel row order = (class, level, post-order):
 //     int32 hdr[16] : 0 n | 1 ncls | 2 nlev | 3 part bytes | 4 off cls_start | 5 off lvl | 6 off row records |
-//                     12,13 bitmask of all-tip-children classes
+//                     7,8 / 9,10 bitmask of the classes whose nodes all have a tip in slot 0 / slot 1
 //     int32 cls_start[ncls + 1]; int32 lvl[ncls][nlev + 1];
 //     record[n], 32 bytes each: real a0, a1; int32 child-0 row, child-1 row, 0, packed (q0 | q1 << 8 | parent code << 16
 //     | class << 24, q = class + 1 of the child or 0 for a tip); the kernel patches the three ints per pair
