@@ -219,10 +219,11 @@ struct Cells {
 // time.  G0 / G1: slot 0 / 1 of the rows has internal children somewhere in this class (otherwise that slot is a tip in
 // every row and its factor is a per-column constant: sigma + lambda against a tip, 1 against an internal node).
 //   C(i,j) = lambda * exp(-((a0-b0)^2 + (a1-b1)^2) / tau) * f0 * f1                       (phyloK2.py:184-199)
-// Software pipeline: the second half of the NEXT group's row records (child-row offsets, store offset, class bytes) is
-// read and its child-cell gathers are issued before the Gaussians of the current group, so the L2 / HBM latency of the
-// gathers is covered; the store offset and parent code of a group ride along in registers (each record half is read
-// once).  Returns the column's partial sum of C over the rows.
+// Software pipeline: the second half of the NEXT group's row records (child-row offsets, class bytes) is read and its
+// child-cell gathers are issued before the Gaussians of the current group, so the L2 / HBM latency of the gathers is
+// covered.  (Measured and dropped: carrying the store offsets in registers instead of re-reading them, predicated
+// gathers that skip the mismatching lanes, gathers two groups ahead: all slower, the loop is sensitive to instruction
+// count and registers.)  Returns the column's partial sum of C over the rows.
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int4 lds_int4(const int4 *p) {     // always one LDS.128 (never split into scalar loads)
     int4 v;
@@ -230,6 +231,9 @@ __device__ __forceinline__ int4 lds_int4(const int4 *p) {     // always one LDS.
     return v;
 }
 
+// child cell of slot 0 / 1: the stored cell when the children's classes agree, else cell 1 (= 1, productions differ)
+#define PK_GATHER0(q) C.ld((((q).w ^ qb0) & 0xff) == 0 ? (q).x + kb0 : 1)
+#define PK_GATHER1(q) C.ld((((q).w ^ qb1) & 0xff00) == 0 ? (q).y + kb1 : 1)
 template <typename T, bool CSMEM, bool G0, bool G1, int U>
 __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0, T b1, int cb0, int cb1, int pkey,
                                      const Cells<T, CSMEM> &C, const GaussK<T> &gk, T sigma, T tipf) {
@@ -240,71 +244,51 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
     if (!G1) cf *= qb1 == 0 ? tipf : (T)1;
     T part = (T)0;
     T f0[U], f1[U];
-    int so[U], pm[U];
     int rr = 0;
     const int4 *ip = reinterpret_cast<const int4 *>(rp);                   // ip[2 r + 1] = {off0, off1, st_off, packed}
-    if (U <= rows) {
+    if ((G0 || G1) && U <= rows) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int4 q = lds_int4(ip + 2 * u + 1);
-            if (G0) f0[u] = C.ld(((q.w ^ qb0) & 0xff) == 0 ? q.x + kb0 : 1);
-            if (G1) f1[u] = C.ld(((q.w ^ qb1) & 0xff00) == 0 ? q.y + kb1 : 1);
-            so[u] = q.z + jb;
-            pm[u] = q.w;
+            if (G0) f0[u] = PK_GATHER0(q);
+            if (G1) f1[u] = PK_GATHER1(q);
         }
     }
     for (; rr + U <= rows; rr += U, rp += U, ip += 2 * U) {
         T x[U], ev[U], g[U];
-        int cso[U], cpm[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
             x[u] = fma(d1, d1, d0 * d0);
             g[u] = G0 ? (G1 ? f0[u] * f1[u] : f0[u] * cf) : (G1 ? f1[u] * cf : cf);
-            cso[u] = so[u];
-            cpm[u] = pm[u];
         }
         if (G0 || G1) {   // always prefetch (the last group re-reads itself: no join, no register copies)
             const int4 *np = rr + 2 * U <= rows ? ip + 2 * U : ip;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int4 q = lds_int4(np + 2 * u + 1);
-                if (G0) f0[u] = C.ld(((q.w ^ qb0) & 0xff) == 0 ? q.x + kb0 : 1);
-                if (G1) f1[u] = C.ld(((q.w ^ qb1) & 0xff00) == 0 ? q.y + kb1 : 1);
-                so[u] = q.z + jb;
-                pm[u] = q.w;
-            }
-        } else {
-            const int4 *np = rr + 2 * U <= rows ? ip + 2 * U : ip;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int2 q = *reinterpret_cast<const int2 *>(reinterpret_cast<const int *>(np + 2 * u + 1) + 2);
-                so[u] = q.x + jb;
-                pm[u] = q.y;
+                if (G0) f0[u] = PK_GATHER0(q);
+                if (G1) f1[u] = PK_GATHER1(q);
             }
         }
         pk_gauss<U>(x, ev, gk);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const T v = ev[u] * g[u];
-#ifdef PK_CARRY
-            if (((cpm[u] ^ pkey) & 0xff0000) == 0) C.st(cso[u], v + sigma);
-#else
             if (((rp[u].packed ^ pkey) & 0xff0000) == 0) C.st(rp[u].st_off + jb, v + sigma);
-#endif
             part += v;
         }
     }
     // the last 1..U-1 rows: all their gathers first (one exposed round trip, not one per row)
     const int rem = rows - rr;
-    if (rem > 0) {
-        T g0[U - 1], g1[U - 1];
+    if (U > 1 && rem > 0) {
+        T g0[U > 1 ? U - 1 : 1], g1[U > 1 ? U - 1 : 1];
 #pragma unroll
         for (int u = 0; u < U - 1; ++u) {
             if (u < rem) {
                 const int4 q = lds_int4(ip + 2 * u + 1);
-                if (G0) g0[u] = C.ld(((q.w ^ qb0) & 0xff) == 0 ? q.x + kb0 : 1);
-                if (G1) g1[u] = C.ld(((q.w ^ qb1) & 0xff00) == 0 ? q.y + kb1 : 1);
+                if (G0) g0[u] = PK_GATHER0(q);
+                if (G1) g1[u] = PK_GATHER1(q);
             }
         }
 #pragma unroll
@@ -332,6 +316,9 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
 #ifndef PK_U2_BOUND
 #define PK_U2_BOUND 256
 #endif
+#ifndef PK_USMALL
+#define PK_USMALL 2
+#endif
 #ifndef PK_MINB
 #define PK_MINB 3
 #endif
@@ -348,7 +335,7 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 192 ? PK_MINB192 : BOUND <= 2
     const int NT = blockDim.x, NW = NT >> 5;       // any multiple of 32 up to BOUND
     // rows in flight per lane: 2 where several CTAs share an SM (more, lighter warps hide the latencies better: measured
     // 445 vs 410 Gcells/s at 500 tips), 4 where one big CTA owns the SM (2000 tips: 417 vs 363)
-    constexpr int U = BOUND <= PK_U2_BOUND ? 2 : PK_UNROLL;
+    constexpr int U = BOUND <= PK_U2_BOUND ? PK_USMALL : PK_UNROLL;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ long long s_work[2];
