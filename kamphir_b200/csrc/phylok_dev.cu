@@ -992,18 +992,18 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
     args.lambda = p->decay;
     args.neg_inv_tau = -1.0 / p->gauss;
     args.sigma = p->sigma;
+    if (!(p->gauss > 0.0)) return pk_fail(PK_ERR_INVALID, "gaussFactor must be positive");
     if (p->decay == 0.0) {
         pk_zero_kernel<<<(int)std::min<long long>((args.total + 255) / 256, 1024), 256, 0, ctx->stream>>>(args);
         PK_CUDA(cudaGetLastError());
         ctx->launches++;
         return PK_OK;
     }
+    if (!(p->decay > 0.0) || p->decay < 1e-200 || p->decay > 1e200)
+        return pk_fail(PK_ERR_INVALID, "decayFactor must be 0 or in [1e-200, 1e200]");
     if (!prec32) {
         // fp64 Gaussian (pk_gauss): table of lambda * 2^(j/64) with the high word biased by -(j << 14), the clamp that
         // keeps lambda * 2^(-E/64) a normal number, and the length scale that turns d^2/tau into 1/64 octaves
-        if (!(p->gauss > 0.0)) return pk_fail(PK_ERR_INVALID, "gaussFactor must be positive");
-        if (!(p->decay > 0.0) || p->decay < 1e-200 || p->decay > 1e200)
-            return pk_fail(PK_ERR_INVALID, "decayFactor must be in [1e-200, 1e200]");
         for (int j = 0; j < 64; ++j) {
             const double t = p->decay * std::exp2((double)j / 64.0);
             unsigned long long bits;

@@ -171,6 +171,38 @@ def test_unladderized_trees_tip_in_either_slot():
     assert rel(got, want) < 1e-9
 
 
+@pytest.mark.parametrize("precision", [64, 32])
+def test_wide_dynamic_range_of_the_gaussian(precision):
+    """Un-normalised trees on very different length scales: exponents from 0 to far beyond exp(-700) in one launch
+    (fp64: the table-based Gaussian clamps its exponent instead of underflowing; the reference's math.exp gives 0)."""
+    import re
+    base = synth.tree_set(4, 120, 8100, "mixed")
+
+    def scaled(nwk, f):
+        return re.sub(r":([0-9.eE+-]+)", lambda m: ":%.10g" % (float(m.group(1)) * f), nwk)
+
+    nwk = [scaled(base[0], 1.0), scaled(base[1], 40.0), scaled(base[2], 0.01), scaled(base[3], 3000.0), scaled(base[0], 40.0)]
+    flats = [FlatTree.from_newick(s, 3, "none") for s in nwk]
+    orac = [oracle_flat(s, "kamphir:none") for s in nwk]
+    for tau in (2.0, 0.05):
+        pk = PhyloKernel(decayFactor=0.2, gaussFactor=tau, normalize="none", precision=precision)
+        got = pk.kernel_batch(flats)
+        want = np.array([[c_oracle.kernel(a, b, 0.2, tau) for b in orac] for a in orac])
+        assert np.all(np.isfinite(got)) and np.all(got >= 0)
+        # relative where the reference is representable, absolute (far below any meaningful K) where it underflows
+        assert np.all(np.abs(got - want) <= TOL[precision] * want + 1e-290)
+
+
+def test_parameter_domain():
+    """gaussFactor must be positive and decayFactor non-negative; decayFactor = 0 gives K = 0 exactly."""
+    a = "((a:1,b:2):1,(c:1,d:3):2);"
+    for kw in (dict(gaussFactor=-1.0), dict(decayFactor=-0.1), dict(gaussFactor=float("nan"))):
+        with pytest.raises(ValueError):
+            PhyloKernel(**kw).kernel(a, a)
+    assert PhyloKernel(decayFactor=0.0).kernel(a, a) == 0.0
+    assert PhyloKernel(decayFactor=0.0, precision=32).kernel(a, a) == 0.0
+
+
 def test_score_batch_matches_kamphir_compute():
     """configs[0]/[1]: one ABC proposal = nreps simulated trees against the observed tree (kamphir.py:249-306,434-450)."""
     obs = synth.kingman_newick(100, 1)
