@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <thread>
 
 #include "phylok_internal.h"
@@ -38,42 +39,44 @@ extern "C" int pk_abi_version(void) { return PK_ABI_VERSION; }
 // ---------------------------------------------------------------------------------------------------
 namespace {
 
+// one node per token-created clade; all fields of a node share a cache line (the parser appends one node per '(' or ',')
+struct RawNode {
+    int32_t parent, first, last, next, nchild, name_off, name_len, pad;
+    double bl;                               // NaN = absent (Biopython: None)
+};
 struct RawTree {
-    std::vector<int32_t> parent, first, last, next, nchild;
-    std::vector<double> bl;                  // NaN = absent (Biopython: None)
-    std::vector<int32_t> name_off, name_len;
+    std::vector<RawNode> nd;
     int32_t root = -1;
 
     int32_t add(int32_t par) {
-        int32_t id = (int32_t)parent.size();
-        parent.push_back(par);
-        first.push_back(-1);
-        last.push_back(-1);
-        next.push_back(-1);
-        nchild.push_back(0);
-        bl.push_back(std::numeric_limits<double>::quiet_NaN());
-        name_off.push_back(0);
-        name_len.push_back(0);
+        const int32_t id = (int32_t)nd.size();
+        nd.push_back(RawNode{par, -1, -1, -1, 0, 0, 0, 0, std::numeric_limits<double>::quiet_NaN()});
         if (par >= 0) link(par, id);
         return id;
     }
     void link(int32_t par, int32_t id) {
-        parent[id] = par;
-        next[id] = -1;
-        if (first[par] < 0) first[par] = id; else next[last[par]] = id;
-        last[par] = id;
-        nchild[par]++;
+        nd[id].parent = par;
+        nd[id].next = -1;
+        RawNode &p = nd[par];
+        if (p.first < 0) p.first = id; else nd[p.last].next = id;
+        p.last = id;
+        p.nchild++;
     }
-    size_t size() const { return parent.size(); }
+    size_t size() const { return nd.size(); }
     void clear() {      // keeps the capacity: one RawTree is reused for every tree a worker parses
-        parent.clear(); first.clear(); last.clear(); next.clear(); nchild.clear();
-        bl.clear(); name_off.clear(); name_len.clear();
+        nd.clear();
         root = -1;
     }
-    void reserve(size_t n) {
-        parent.reserve(n); first.reserve(n); last.reserve(n); next.reserve(n); nchild.reserve(n);
-        bl.reserve(n); name_off.reserve(n); name_len.reserve(n);
-    }
+    void reserve(size_t n) { nd.reserve(n); }
+};
+
+// per-worker scratch of flatten(): capacities survive from tree to tree
+struct Scratch {
+    RawTree raw;
+    std::vector<int32_t> pre, stack, ntip, kids, post, pidx;
+    std::vector<double> depth, lens;
+    std::vector<std::pair<int32_t, int32_t>> st;
+    std::string err;
 };
 
 inline bool is_punct(char c) {
@@ -98,7 +101,7 @@ int parse_one(const char *text, size_t b, size_t e, RawTree &t, std::string &err
             cur = t.add(cur);
             ++lp; ++i;
         } else if (ch == ',') {
-            int32_t par = t.parent[cur];
+            int32_t par = t.nd[cur].parent;
             if (par < 0) {                 // outer parentheses missing: new root above the current clade
                 int32_t nr = t.add(-1);
                 t.link(nr, cur);
@@ -109,7 +112,7 @@ int parse_one(const char *text, size_t b, size_t e, RawTree &t, std::string &err
             cur = t.add(par);
             ++i;
         } else if (ch == ')') {
-            int32_t par = t.parent[cur];
+            int32_t par = t.nd[cur].parent;
             if (par < 0) { err = "Newick: parenthesis mismatch"; return PK_ERR_PARSE; }
             cur = par;
             ++rp; ++i;
@@ -126,14 +129,14 @@ int parse_one(const char *text, size_t b, size_t e, RawTree &t, std::string &err
                 err = "Newick: bad branch length '" + std::string(text + j, k - j) + "'";
                 return PK_ERR_PARSE;
             }
-            t.bl[cur] = v;
+            t.nd[cur].bl = v;
             i = k;
         } else if (ch == '\'') {
             size_t j = i + 1;
             while (j < e && text[j] != '\'') ++j;
             if (j >= e) { err = "Newick: unterminated quoted label"; return PK_ERR_PARSE; }
-            t.name_off[cur] = (int32_t)(i + 1 - b);
-            t.name_len[cur] = (int32_t)(j - i - 1);
+            t.nd[cur].name_off = (int32_t)(i + 1 - b);
+            t.nd[cur].name_len = (int32_t)(j - i - 1);
             i = j + 1;
         } else if (ch == '[') {
             size_t j = i + 1;
@@ -148,13 +151,13 @@ int parse_one(const char *text, size_t b, size_t e, RawTree &t, std::string &err
         } else {
             size_t k = i;
             while (k < e && !is_punct(text[k]) && !is_space(text[k])) ++k;
-            t.name_off[cur] = (int32_t)(i - b);
-            t.name_len[cur] = (int32_t)(k - i);
+            t.nd[cur].name_off = (int32_t)(i - b);
+            t.nd[cur].name_len = (int32_t)(k - i);
             i = k;
         }
     }
     if (lp != rp) { err = "Newick: number of open/close parentheses do not match"; return PK_ERR_PARSE; }
-    if (cur != t.root && !(synthetic_root && t.parent[cur] == t.root)) {
+    if (cur != t.root && !(synthetic_root && t.nd[cur].parent == t.root)) {
         err = "Newick: parenthesis mismatch";
         return PK_ERR_PARSE;
     }
@@ -170,6 +173,16 @@ void split_trees(const char *text, size_t len, std::vector<std::pair<size_t, siz
         while (z > a && is_space(text[z - 1])) --z;
         if (z > a) out.emplace_back(a, z);
     };
+    if (!std::memchr(text, '\'', len) && !std::memchr(text, '[', len)) {   // no quotes, no comments: every ';' separates
+        while (i < len) {
+            const char *q = static_cast<const char *>(std::memchr(text + i, ';', len - i));
+            if (!q) break;
+            flush((size_t)(q - text));
+            start = i = (size_t)(q - text) + 1;
+        }
+        flush(len);
+        return;
+    }
     while (i < len) {
         char ch = text[i];
         if (ch == '\'') {
@@ -194,8 +207,8 @@ void split_trees(const char *text, size_t len, std::vector<std::pair<size_t, siz
 }
 
 int tip_state(const char *text, const RawTree &t, int32_t v, int nstates, int &state, std::string &err) {
-    const char *p = text + t.name_off[v];
-    int len = t.name_len[v];
+    const char *p = text + t.nd[v].name_off;
+    int len = t.nd[v].name_len;
     int k = len;
     while (k > 0 && p[k - 1] != '_') --k;          // token after the last '_'  (rcolgem.py:274)
     int val = 0;
@@ -210,16 +223,15 @@ int tip_state(const char *text, const RawTree &t, int32_t v, int nstates, int &s
 }
 
 // RawTree -> pk_tree following kamphir's prep order.
-int flatten(const char *text, RawTree &r, int flags, int normalize, int nstates, pk_tree &out, std::string &err) {
+int flatten(const char *text, Scratch &sc, int flags, int normalize, int nstates, pk_tree &out, std::string &err) {
+    RawTree &r = sc.raw;
+    std::vector<RawNode> &nd = r.nd;
     const int32_t total = (int32_t)r.size();
     const int32_t root = r.root;
     const double NaN = std::numeric_limits<double>::quiet_NaN();
 
-    // pre-order (node, then children in order) and its reverse for bottom-up passes
-    std::vector<int32_t> pre;
-    pre.reserve(total);
-    std::vector<int32_t> stack;
-    stack.reserve(64);
+    // pre-order (node, then children in order); its reverse serves the bottom-up passes
+    std::vector<int32_t> &pre = sc.pre, &stack = sc.stack;
     auto preorder = [&]() {
         pre.clear();
         stack.clear();
@@ -229,60 +241,67 @@ int flatten(const char *text, RawTree &r, int flags, int normalize, int nstates,
             stack.pop_back();
             pre.push_back(v);
             const size_t base = stack.size();
-            for (int32_t c = r.first[v]; c >= 0; c = r.next[c]) stack.push_back(c);
+            for (int32_t c = nd[v].first; c >= 0; c = nd[c].next) stack.push_back(c);
             std::reverse(stack.begin() + base, stack.end());
         }
     };
     preorder();
 
-    if (flags & PK_PREP_ZERO_ROOT) r.bl[root] = 0.0;                       // kamphir.py:153,279
+    if (flags & PK_PREP_ZERO_ROOT) nd[root].bl = 0.0;                      // kamphir.py:153,279
 
     if (flags & PK_PREP_LADDERIZE) {                                       // kamphir.py:154,280
-        std::vector<int32_t> ntip(total, 0);
+        std::vector<int32_t> &ntip = sc.ntip;
+        ntip.assign(total, 0);
         for (size_t k = pre.size(); k-- > 0;) {
             int32_t v = pre[k];
-            if (r.first[v] < 0) ntip[v] = 1;
-            if (r.parent[v] >= 0) ntip[r.parent[v]] += ntip[v];
+            if (nd[v].first < 0) ntip[v] = 1;
+            if (nd[v].parent >= 0) ntip[nd[v].parent] += ntip[v];
         }
-        std::vector<int32_t> kids;
+        bool changed = false;
+        std::vector<int32_t> &kids = sc.kids;
         for (int32_t v = 0; v < total; ++v) {
-            if (r.nchild[v] < 2) continue;
-            if (r.nchild[v] == 2) {        // binary node: swap only when strictly larger first (stable on ties)
-                const int32_t x = r.first[v], y = r.next[x];
+            if (nd[v].nchild < 2) continue;
+            if (nd[v].nchild == 2) {       // binary node: swap only when strictly larger first (stable on ties)
+                const int32_t x = nd[v].first, y = nd[x].next;
                 if (ntip[x] > ntip[y]) {
-                    r.first[v] = y;
-                    r.next[y] = x;
-                    r.next[x] = -1;
-                    r.last[v] = x;
+                    nd[v].first = y;
+                    nd[y].next = x;
+                    nd[x].next = -1;
+                    nd[v].last = x;
+                    changed = true;
                 }
                 continue;
             }
             kids.clear();
-            for (int32_t c = r.first[v]; c >= 0; c = r.next[c]) kids.push_back(c);
+            for (int32_t c = nd[v].first; c >= 0; c = nd[c].next) kids.push_back(c);
             std::stable_sort(kids.begin(), kids.end(), [&](int32_t a, int32_t b) { return ntip[a] < ntip[b]; });
-            r.first[v] = kids.front();
-            r.last[v] = kids.back();
-            for (size_t k = 0; k < kids.size(); ++k) r.next[kids[k]] = (k + 1 < kids.size()) ? kids[k + 1] : -1;
+            nd[v].first = kids.front();
+            nd[v].last = kids.back();
+            for (size_t k = 0; k < kids.size(); ++k) nd[kids[k]].next = (k + 1 < kids.size()) ? kids[k + 1] : -1;
+            changed = true;
         }
-        preorder();
+        if (changed) preorder();
     }
 
-    // un-normalised depths / node heights (kamphir.py:118-119,147-149,255-258); None counts as 0
+    // un-normalised depths / node heights (kamphir.py:118-119,147-149,255-258); None counts as 0.  The heights are kept
+    // unsorted here; pk_sorted_heights() sorts them the first time kcoal asks.
     {
-        std::vector<double> depth(total, 0.0);
+        std::vector<double> &depth = sc.depth;
+        depth.assign(total, 0.0);
         double hmax = 0.0;
         bool firstv = true;
         for (int32_t v : pre) {
-            double b = std::isnan(r.bl[v]) ? 0.0 : r.bl[v];
-            depth[v] = (r.parent[v] >= 0 ? depth[r.parent[v]] : 0.0) + b;
+            double b = std::isnan(nd[v].bl) ? 0.0 : nd[v].bl;
+            depth[v] = (nd[v].parent >= 0 ? depth[nd[v].parent] : 0.0) + b;
             if (firstv || depth[v] > hmax) hmax = depth[v];
             firstv = false;
         }
         out.height = hmax;
         out.heights.clear();
+        out.heights.reserve((size_t)total / 2 + 1);
         for (int32_t v : pre)
-            if (r.first[v] >= 0) out.heights.push_back(hmax - depth[v]);
-        std::sort(out.heights.begin(), out.heights.end());
+            if (nd[v].first >= 0) out.heights.push_back(hmax - depth[v]);
+        out.heights_sorted = false;
     }
 
     // normalize_tree (phyloK2.py:101-130): every non-root branch divided by the mean / median
@@ -294,18 +313,19 @@ int flatten(const char *text, RawTree &r, int flags, int normalize, int nstates,
         if (normalize == PK_NORM_MEAN) {
             double sum = 0.0;                                              // total_branch_length(): truthy lengths, pre-order
             for (int32_t v : pre) {
-                double b = r.bl[v];
+                double b = nd[v].bl;
                 if (!std::isnan(b) && b != 0.0) sum = sum + b;
             }
-            double rootbl = std::isnan(r.bl[root]) ? 0.0 : r.bl[root];     // reference: TypeError on None (phyloK2.py:113)
+            double rootbl = std::isnan(nd[root].bl) ? 0.0 : nd[root].bl;   // reference: TypeError on None (phyloK2.py:113)
             scale = (sum - rootbl) / nbranches;
         } else {
-            std::vector<double> lens;
+            std::vector<double> &lens = sc.lens;
+            lens.clear();
             lens.reserve(nbranches);
             for (int32_t v : pre) {
                 if (v == root) continue;
-                if (std::isnan(r.bl[v])) { err = "normalize_tree: branch without a length"; return PK_ERR_INVALID; }
-                lens.push_back(r.bl[v]);
+                if (std::isnan(nd[v].bl)) { err = "normalize_tree: branch without a length"; return PK_ERR_INVALID; }
+                lens.push_back(nd[v].bl);
             }
             std::sort(lens.begin(), lens.end());
             int32_t half = nbranches / 2;                                  // py2 integer division, :123-127
@@ -316,7 +336,7 @@ int flatten(const char *text, RawTree &r, int flags, int normalize, int nstates,
             return PK_ERR_INVALID;
         }
         for (int32_t v = 0; v < total; ++v)
-            if (v != root && !std::isnan(r.bl[v])) r.bl[v] /= scale;
+            if (v != root && !std::isnan(nd[v].bl)) nd[v].bl /= scale;
         out.scale = scale;
     } else if (normalize != PK_NORM_NONE) {
         err = "unknown normalize mode";
@@ -324,28 +344,31 @@ int flatten(const char *text, RawTree &r, int flags, int normalize, int nstates,
     }
 
     // annotate_tree (phyloK2.py:132-146): internal nodes in post-order
-    std::vector<int32_t> post;
+    std::vector<int32_t> &post = sc.post;
+    post.clear();
     post.reserve(total);
     {
         // iterative post-order: children (in order) before the parent
-        std::vector<std::pair<int32_t, int32_t>> st;   // (node, next child to visit)
-        st.emplace_back(root, r.first[root]);
+        std::vector<std::pair<int32_t, int32_t>> &st = sc.st;   // (node, next child to visit)
+        st.clear();
+        st.emplace_back(root, nd[root].first);
         while (!st.empty()) {
             auto &top = st.back();
             if (top.second >= 0) {
                 int32_t c = top.second;
-                top.second = r.next[c];
-                st.emplace_back(c, r.first[c]);
+                top.second = nd[c].next;
+                st.emplace_back(c, nd[c].first);
             } else {
                 post.push_back(top.first);
                 st.pop_back();
             }
         }
     }
-    std::vector<int32_t> pidx(total, -1);
+    std::vector<int32_t> &pidx = sc.pidx;
+    pidx.assign(total, -1);
     int32_t n = 0, ntips = 0;
     for (int32_t v : post) {
-        if (r.first[v] >= 0) pidx[v] = n++; else ++ntips;
+        if (nd[v].first >= 0) pidx[v] = n++; else ++ntips;
     }
     if (n == 0) { err = "tree has no internal node (reference: IndexError at phyloK2.py:169)"; return PK_ERR_INVALID; }
     out.n = n;
@@ -358,25 +381,25 @@ int flatten(const char *text, RawTree &r, int flags, int normalize, int nstates,
     out.cidx.assign(2 * (size_t)n, -1);
     out.bl.assign(2 * (size_t)n, NaN);
     for (int32_t v : post) {
-        if (r.first[v] < 0) continue;
+        if (nd[v].first < 0) continue;
         int32_t i = pidx[v];
-        if (r.nchild[v] != 2) {
-            err = "internal node " + std::to_string(i) + " has " + std::to_string(r.nchild[v]) +
+        if (nd[v].nchild != 2) {
+            err = "internal node " + std::to_string(i) + " has " + std::to_string(nd[v].nchild) +
                   " children; the kernel is defined for strictly binary trees (reference: IndexError at phyloK2.py:185-189)";
             return PK_ERR_INVALID;
         }
-        int32_t kid[2] = {r.first[v], r.next[r.first[v]]};
+        int32_t kid[2] = {nd[v].first, nd[nd[v].first].next};
         int nterm = 0, st[2] = {-1, -1};
         for (int s = 0; s < 2; ++s) {
             int32_t c = kid[s];
-            double b = r.bl[c];
+            double b = nd[c].bl;
             if (!std::isfinite(b)) {
                 err = std::isnan(b) ? "branch without a length (reference: TypeError at phyloK2.py:146)"
                                     : "non-finite branch length";
                 return PK_ERR_INVALID;
             }
             out.bl[2 * (size_t)i + s] = b;
-            if (r.first[c] < 0) {
+            if (nd[c].first < 0) {
                 ++nterm;
                 if (nstates > 0) {
                     int rc = tip_state(text, r, c, nstates, st[s], err);
@@ -463,22 +486,29 @@ int pk_tree_finish(pk_tree &t) {
     t.colorder.assign(n, 0);
     t.krank.assign(n, 0);
     {
-        constexpr int kPath = 5;
-        std::vector<std::pair<uint64_t, int32_t>> keys(n);
-        for (int32_t i = 0; i < n; ++i) {
-            uint64_t k = t.cls[i];
-            int32_t v = i;
-            for (int d = 0; d < kPath; ++d) {
-                k = (k << 8) | (v >= 0 ? t.pcode[v] : 0);
-                if (v >= 0) v = parent[v];
+        // counting sort into the (class, parent code) groups (stable in post-order), then each small group by the
+        // parent codes of the next four ancestors (ties keep the post-order)
+        std::vector<int32_t> fill(t.gstart.begin(), t.gstart.end() - 1);
+        for (int32_t i = 0; i < n; ++i) t.colorder[fill[(size_t)t.cls[i] * npc + t.pcode[i]]++] = i;
+        std::vector<std::pair<uint32_t, int32_t>> keys;
+        for (size_t g = 0; g + 1 < t.gstart.size(); ++g) {
+            const int32_t lo = t.gstart[g], hi = t.gstart[g + 1];
+            if (hi - lo > 1) {
+                keys.resize((size_t)(hi - lo));
+                for (int32_t c = lo; c < hi; ++c) {
+                    const int32_t i = t.colorder[c];
+                    uint32_t k = 0;
+                    int32_t v = parent[i];
+                    for (int d = 0; d < 4; ++d) {
+                        k = (k << 8) | (v >= 0 ? t.pcode[v] : 0);
+                        if (v >= 0) v = parent[v];
+                    }
+                    keys[(size_t)(c - lo)] = {k, i};
+                }
+                std::sort(keys.begin(), keys.end());
+                for (int32_t c = lo; c < hi; ++c) t.colorder[c] = keys[(size_t)(c - lo)].second;
             }
-            keys[i] = {k, i};
-        }
-        std::sort(keys.begin(), keys.end());
-        for (int32_t col = 0; col < n; ++col) {
-            const int32_t i = keys[col].second;
-            t.colorder[col] = i;
-            t.krank[i] = col - t.gstart[(size_t)t.cls[i] * npc + t.pcode[i]];
+            for (int32_t c = lo; c < hi; ++c) t.krank[t.colorder[c]] = c - lo;
         }
     }
     t.hist.assign((size_t)ncls * 2 * (ncls + 1), 0);
@@ -618,13 +648,14 @@ extern "C" int pk_tree_from_newick(const char *text, size_t len, int prep_flags,
     split_trees(text, len, ranges);
     if (ranges.size() != 1)
         return pk_fail(PK_ERR_PARSE, "expected exactly one tree, found " + std::to_string(ranges.size()));
-    RawTree raw;
+    static thread_local Scratch sc;
+    RawTree &raw = sc.raw;
     std::string err;
     int rc = parse_one(text, ranges[0].first, ranges[0].second, raw, err);
     if (rc != PK_OK) return pk_fail(rc, err);
     pk_tree *t = new (std::nothrow) pk_tree();
     if (!t) return pk_fail(PK_ERR_NOMEM, "out of memory");
-    rc = flatten(text + ranges[0].first, raw, prep_flags, normalize, n_states, *t, err);
+    rc = flatten(text + ranges[0].first, sc, prep_flags, normalize, n_states, *t, err);
     if (rc != PK_OK) {
         delete t;
         return pk_fail(rc, err.empty() ? std::string(pk_last_error()) : err);
@@ -682,7 +713,8 @@ static int flatten_many(const std::vector<const char *> &bases, const std::vecto
     std::string first_err;
     std::atomic<bool> have_err{false};
     auto worker = [&]() {
-        RawTree raw;
+        Scratch sc;
+        RawTree &raw = sc.raw;
         std::string err;
         for (;;) {
             size_t k = next.fetch_add(1);
@@ -692,7 +724,7 @@ static int flatten_many(const std::vector<const char *> &bases, const std::vecto
             if (rc == PK_OK) {
                 arr[k] = new (std::nothrow) pk_tree();
                 if (!arr[k]) { rc = PK_ERR_NOMEM; err = "out of memory"; }
-                else rc = flatten(text + ranges[k].first, raw, prep_flags, normalize, n_states, *arr[k], err);
+                else rc = flatten(text + ranges[k].first, sc, prep_flags, normalize, n_states, *arr[k], err);
             }
             if (rc != PK_OK) {
                 bool expected = false;
@@ -799,10 +831,20 @@ extern "C" int pk_tree_export(const pk_tree *t, uint8_t *prod, uint8_t *cprod, i
     return PK_OK;
 }
 
+// ascending node heights (kamphir.py:257-258 sorts them); sorted on first use, under the tree's once-flag
+static const std::vector<double> &pk_sorted_heights(const pk_tree *t) {
+    pk_tree *m = const_cast<pk_tree *>(t);
+    std::call_once(m->heights_once, [m]() {
+        if (!m->heights_sorted) std::sort(m->heights.begin(), m->heights.end());
+        m->heights_sorted = true;
+    });
+    return t->heights;
+}
+
 extern "C" int pk_tree_node_heights(const pk_tree *t, double *heights) {
     if (!t || !heights) return pk_fail(PK_ERR_INVALID, "null argument");
     if ((int32_t)t->heights.size() != t->n) return pk_fail(PK_ERR_INVALID, "tree was built from arrays: no node heights");
-    std::memcpy(heights, t->heights.data(), sizeof(double) * (size_t)t->n);
+    std::memcpy(heights, pk_sorted_heights(t).data(), sizeof(double) * (size_t)t->n);
     return PK_OK;
 }
 
@@ -829,9 +871,10 @@ extern "C" int pk_kcoal(const pk_tree *sim, const pk_tree *target, double *out) 
         return pk_fail(PK_ERR_INVALID, "node heights unavailable (tree built from arrays)");
     if (sim->n > target->n)
         return pk_fail(PK_ERR_INVALID, "simulated tree has more internal nodes than the target (reference: IndexError at kamphir.py:264)");
+    const std::vector<double> &hs = pk_sorted_heights(sim), &ht = pk_sorted_heights(target);
     double dot = 0, n1 = 0, n2 = 0;                                          // kamphir.py:260-269
     for (int32_t k = 0; k < sim->n; ++k) {
-        double h = sim->heights[k], g = target->heights[k];
+        double h = hs[k], g = ht[k];
         dot += h * g;
         n1 += h * h;
         n2 += g * g;

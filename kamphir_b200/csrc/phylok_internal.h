@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cstddef>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -33,7 +34,9 @@ struct pk_tree {
     std::vector<int32_t> cls_start; // [ncls + 1]
     std::vector<int32_t> lvl;       // [ncls * (nlev + 1)]  absolute first kernel row of level L in class c
     std::vector<int64_t> hist;      // [ncls * 2 * (ncls + 1)]  nodes of class c whose slot-s child has class q (0 = tip)
-    std::vector<double> heights;    // [n]   ascending node heights, un-normalised
+    std::vector<double> heights;    // [n]   node heights, un-normalised; ascending once heights_sorted (first kcoal use)
+    bool heights_sorted = false;
+    std::once_flag heights_once;
     // column order: nodes sorted by (class, parent code, parent codes of the next ancestors, post-order).  The parent code of a node is
     // (class of its parent + 1) * 2 + its slot in the parent (0 for the root).  A C cell (i, j) is read -- by the cell of
     // the two parents -- only when i and j have the same parent code, so with this order the cells of row i that are
