@@ -102,6 +102,8 @@ int pk_tree_node_heights(const pk_tree *t, double *heights /* n_internal */);
 int pk_pair_counts(const pk_tree *a, const pk_tree *b, int64_t counts[3]);
 /* kcoal of kamphir.py:260-269: cosine of the two ascending node-height vectors (sim indexed into target) */
 int pk_kcoal(const pk_tree *sim, const pk_tree *target, double *out);
+/* the same for every replicate of one proposal (kamphir.py:434-450 loops over them): out[s] = kcoal(sims[s], target) */
+int pk_kcoal_batch(const pk_tree *const *sims, int32_t nsims, const pk_tree *target, double *out);
 
 /* ---- device side ------------------------------------------------------------------------------------ */
 int pk_ctx_create(int device, pk_ctx **out);

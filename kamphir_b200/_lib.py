@@ -44,6 +44,7 @@ SIGNATURES = {
     "pk_tree_node_heights": (ctypes.c_int, [_P, _P]),
     "pk_pair_counts": (ctypes.c_int, [_P, _P, _P]),
     "pk_kcoal": (ctypes.c_int, [_P, _P, ctypes.POINTER(_D)]),
+    "pk_kcoal_batch": (ctypes.c_int, [_P, _I32, _P, _P]),
     "pk_ctx_create": (ctypes.c_int, [ctypes.c_int, _PP]),
     "pk_ctx_destroy": (None, [_P]),
     "pk_ctx_set_stream": (ctypes.c_int, [_P, _P]),

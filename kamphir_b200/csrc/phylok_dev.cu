@@ -25,8 +25,10 @@
 #include <cstdio>
 #include <cstring>
 #include <atomic>
+#include <map>
 #include <string>
 #include <thread>
+#include <tuple>
 #include <vector>
 
 #include "phylok_internal.h"
@@ -612,6 +614,8 @@ struct pk_ctx {
     long long launches = 0;
     int last_path = 0;
     int last_grid = 0, last_threads = 0, last_smem = 0;
+    std::map<std::tuple<int, int, int>, int> attr_smem;             // kernel variant -> dynamic shared-memory limit set
+    std::map<std::tuple<int, int, int, int, int>, int> occupancy;   // (variant, threads, smem) -> resident CTAs per SM
 };
 
 struct pk_forest {
@@ -870,24 +874,16 @@ extern "C" int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_
         }
     };
     {
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        const int nthr = (int)std::min<size_t>(std::min<size_t>(hw, 32), std::max<size_t>(1, total / ((size_t)2 << 20)));
-        if (nthr <= 1) {
-            pack_range(0, n);
-        } else {
-            std::vector<std::thread> pool;
-            std::atomic<int32_t> next{0};
-            const int32_t chunk = std::max<int32_t>(1, n / (nthr * 8));
-            for (int k = 0; k < nthr; ++k)
-                pool.emplace_back([&]() {
-                    for (;;) {
-                        const int32_t lo = next.fetch_add(chunk);
-                        if (lo >= n) break;
-                        pack_range(lo, std::min(n, lo + chunk));
-                    }
-                });
-            for (auto &th : pool) th.join();
-        }
+        const int nthr = (int)std::min<size_t>(std::min(pk_host_threads(), 32), std::max<size_t>(1, total / ((size_t)1 << 20)));
+        std::atomic<int32_t> next{0};
+        const int32_t chunk = std::max<int32_t>(1, n / (nthr * 8));
+        pk_parallel(nthr, [&](int) {
+            for (;;) {
+                const int32_t lo = next.fetch_add(chunk);
+                if (lo >= n) break;
+                pack_range(lo, std::min(n, lo + chunk));
+            }
+        });
     }
     for (int32_t i = 0; i < n; ++i) {
         const pk_tree &t = *trees[i];
@@ -974,19 +970,37 @@ extern "C" int pk_forest_pair_stats(const pk_forest *fa, const pk_forest *fb, co
 // ---------------------------------------------------------------------------------------------------
 // launch
 // ---------------------------------------------------------------------------------------------------
+// The dynamic shared-memory limit of a kernel variant is raised once per size and its occupancy is queried once per
+// (CTA size, shared memory): a sim-vs-obs proposal is one 30 us launch, the driver calls would cost more than that.
 template <typename T, bool CSMEM, int BOUND>
-static cudaError_t launch_t(const DpArgs &args, int grid, int nt, int smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(pk_dp_kernel<T, CSMEM, BOUND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
+static cudaError_t launch_t(pk_ctx *ctx, const DpArgs &args, int grid, int nt, int smem, cudaStream_t stream) {
+    int &have = ctx->attr_smem[{(int)sizeof(T), (int)CSMEM, BOUND}];
+    if (smem > have) {
+        cudaError_t e = cudaFuncSetAttribute(pk_dp_kernel<T, CSMEM, BOUND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        have = smem;
+    }
     pk_dp_kernel<T, CSMEM, BOUND><<<grid, nt, smem, stream>>>(args);
     return cudaGetLastError();
 }
 
 template <typename T, bool CSMEM, int BOUND>
-static cudaError_t occupancy_t(int nt, int smem, int *blocks) {
-    cudaError_t e = cudaFuncSetAttribute(pk_dp_kernel<T, CSMEM, BOUND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, pk_dp_kernel<T, CSMEM, BOUND>, nt, smem);
+static cudaError_t occupancy_t(pk_ctx *ctx, int nt, int smem, int *blocks) {
+    auto key = std::make_tuple((int)sizeof(T), (int)CSMEM, BOUND, nt, smem);
+    auto it = ctx->occupancy.find(key);
+    if (it != ctx->occupancy.end()) {
+        *blocks = it->second;
+        return cudaSuccess;
+    }
+    int &have = ctx->attr_smem[{(int)sizeof(T), (int)CSMEM, BOUND}];
+    if (smem > have) {
+        cudaError_t e = cudaFuncSetAttribute(pk_dp_kernel<T, CSMEM, BOUND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        have = smem;
+    }
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, pk_dp_kernel<T, CSMEM, BOUND>, nt, smem);
+    if (e == cudaSuccess) ctx->occupancy[key] = *blocks;
+    return e;
 }
 
 // register budgets: <= 224 threads: 72 registers (4 CTAs of 7 warps per SM), <= 256: 80 (3 CTAs), <= 384: 80 (2 CTAs),
@@ -1099,11 +1113,11 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
     // L2-resident anyway and more pairs per SM hide the level barriers better (measured: profiles/r01_summary.md)
     bool csmem = false;
     int smem = (int)base_smem, per_sm = 0;
-    cudaError_t e = PK_DISPATCH(occupancy_t, nt, smem, &per_sm);
+    cudaError_t e = PK_DISPATCH(occupancy_t, ctx, nt, smem, &per_sm);
     if (e == cudaSuccess && ctx->cfg_force_hbm != 1 && base_smem + c_bytes <= limit) {
         int occ_smem = 0;
         csmem = true;
-        e = PK_DISPATCH(occupancy_t, nt, (int)(base_smem + c_bytes), &occ_smem);
+        e = PK_DISPATCH(occupancy_t, ctx, nt, (int)(base_smem + c_bytes), &occ_smem);
         if (e == cudaSuccess && (occ_smem >= per_sm || ctx->cfg_force_hbm == 2)) {
             smem = (int)(base_smem + c_bytes);
             per_sm = occ_smem;
@@ -1125,7 +1139,7 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
     args.counter = ctx->d_counters + (ctx->counter_next++ % kCounterRing);
     PK_CUDA(cudaMemsetAsync(args.counter, 0, sizeof(unsigned long long), ctx->stream));
     PK_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-    e = PK_DISPATCH(launch_t, args, grid, nt, smem, ctx->stream);
+    e = PK_DISPATCH(launch_t, ctx, args, grid, nt, smem, ctx->stream);
     if (e != cudaSuccess) return pk_fail(PK_ERR_CUDA, std::string("DP kernel launch: ") + cudaGetErrorString(e));
     PK_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->ev_valid = true;

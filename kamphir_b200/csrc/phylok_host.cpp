@@ -15,8 +15,12 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <pthread.h>
 #include <thread>
+#include <vector>
 
 #include "phylok_internal.h"
 
@@ -33,6 +37,86 @@ int pk_fail(int code, const std::string &msg) {
 
 extern "C" const char *pk_last_error(void) { return g_err.c_str(); }
 extern "C" int pk_abi_version(void) { return PK_ABI_VERSION; }
+
+// ---------------------------------------------------------------------------------------------------
+// worker pool
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct WorkPool {
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cv_work, cv_done;
+    const std::function<void(int)> *job = nullptr;
+    unsigned long generation = 0;
+    int wanted = 0;      // pool threads that take part in the current job (ids 1..wanted)
+    int pending = 0;
+    std::mutex run_lock; // one job at a time
+
+    explicit WorkPool(int n) {
+        for (int i = 0; i < n; ++i) threads.emplace_back([this, i]() { loop(i + 1); });
+    }
+    void loop(int id) {
+        unsigned long seen = 0;
+        for (;;) {
+            const std::function<void(int)> *fn;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv_work.wait(lk, [&]() { return generation != seen; });
+                seen = generation;
+                if (id > wanted) continue;
+                fn = job;
+            }
+            (*fn)(id);
+            {
+                std::lock_guard<std::mutex> lk(m);
+                if (--pending == 0) cv_done.notify_one();
+            }
+        }
+    }
+    void run(int workers, const std::function<void(int)> &fn) {
+        std::lock_guard<std::mutex> serial(run_lock);
+        const int extra = std::min<int>(workers - 1, (int)threads.size());
+        if (extra > 0) {
+            std::lock_guard<std::mutex> lk(m);
+            job = &fn;
+            wanted = extra;
+            pending = extra;
+            ++generation;
+        }
+        if (extra > 0) cv_work.notify_all();
+        fn(0);
+        if (extra > 0) {
+            std::unique_lock<std::mutex> lk(m);
+            cv_done.wait(lk, [&]() { return pending == 0; });
+        }
+    }
+};
+std::atomic<WorkPool *> g_pool{nullptr};
+std::mutex g_pool_make;
+std::once_flag g_atfork_once;
+}  // namespace
+
+int pk_host_threads() { return (int)std::max(1u, std::thread::hardware_concurrency()); }
+
+void pk_parallel(int workers, const std::function<void(int)> &fn) {
+    if (workers <= 1) {
+        fn(0);
+        return;
+    }
+    WorkPool *p = g_pool.load(std::memory_order_acquire);
+    if (!p) {
+        std::lock_guard<std::mutex> lk(g_pool_make);
+        p = g_pool.load(std::memory_order_acquire);
+        if (!p) {
+            // after fork() the parent's pool threads do not exist in the child: forget the pool (leaked on purpose,
+            // its mutexes may be in any state) and let the child build its own
+            std::call_once(g_atfork_once, []() { pthread_atfork(nullptr, nullptr, []() { g_pool.store(nullptr); }); });
+            p = new WorkPool(std::min(pk_host_threads(), 64) - 1);
+            g_pool.store(p, std::memory_order_release);
+        }
+    }
+    p->run(workers, fn);
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Newick
@@ -283,8 +367,7 @@ int flatten(const char *text, Scratch &sc, int flags, int normalize, int nstates
         if (changed) preorder();
     }
 
-    // un-normalised depths / node heights (kamphir.py:118-119,147-149,255-258); None counts as 0.  The heights are kept
-    // unsorted here; pk_sorted_heights() sorts them the first time kcoal asks.
+    // un-normalised depths / node heights (kamphir.py:118-119,147-149,255-258); None counts as 0
     {
         std::vector<double> &depth = sc.depth;
         depth.assign(total, 0.0);
@@ -301,7 +384,8 @@ int flatten(const char *text, Scratch &sc, int flags, int normalize, int nstates
         out.heights.reserve((size_t)total / 2 + 1);
         for (int32_t v : pre)
             if (nd[v].first >= 0) out.heights.push_back(hmax - depth[v]);
-        out.heights_sorted = false;
+        std::sort(out.heights.begin(), out.heights.end());   // here, on the worker: kamphir's compute() always uses kcoal
+        out.heights_sorted = true;
     }
 
     // normalize_tree (phyloK2.py:101-130): every non-root branch divided by the mean / median
@@ -705,15 +789,15 @@ static int flatten_many(const std::vector<const char *> &bases, const std::vecto
     const size_t nt = ranges.size();
     pk_tree **arr = new (std::nothrow) pk_tree *[nt + 1]();
     if (!arr) return pk_fail(PK_ERR_NOMEM, "out of memory");
-    if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
-    // a worker per ~64 KB of text: spawning threads costs more than parsing a small batch
-    nthreads = (int)std::min<size_t>((size_t)nthreads, std::max<size_t>(1, std::min<size_t>(nt, len / (64 * 1024))));
+    if (nthreads <= 0) nthreads = pk_host_threads();
+    // a worker per ~16 KB of text (waking a parked pool thread costs about as much as parsing that)
+    nthreads = (int)std::min<size_t>((size_t)nthreads, std::max<size_t>(1, std::min<size_t>(nt, len / (16 * 1024))));
     std::atomic<size_t> next{0};
     std::atomic<int> status{PK_OK};
     std::string first_err;
     std::atomic<bool> have_err{false};
-    auto worker = [&]() {
-        Scratch sc;
+    auto worker = [&](int) {
+        static thread_local Scratch sc;
         RawTree &raw = sc.raw;
         std::string err;
         for (;;) {
@@ -736,13 +820,7 @@ static int flatten_many(const std::vector<const char *> &bases, const std::vecto
             }
         }
     };
-    if (nthreads <= 1) {
-        worker();
-    } else {
-        std::vector<std::thread> pool;
-        for (int i = 0; i < nthreads; ++i) pool.emplace_back(worker);
-        for (auto &th : pool) th.join();
-    }
+    pk_parallel(nthreads, worker);
     if (status.load() != PK_OK) {
         for (size_t k = 0; k < nt; ++k) delete arr[k];
         delete[] arr;
@@ -880,5 +958,15 @@ extern "C" int pk_kcoal(const pk_tree *sim, const pk_tree *target, double *out) 
         n2 += g * g;
     }
     *out = dot / (std::sqrt(n1) * std::sqrt(n2));
+    return PK_OK;
+}
+
+extern "C" int pk_kcoal_batch(const pk_tree *const *sims, int32_t nsims, const pk_tree *target, double *out) {
+    if (!sims || !target || (nsims > 0 && !out)) return pk_fail(PK_ERR_INVALID, "null argument");
+    for (int32_t s = 0; s < nsims; ++s) {
+        if (!sims[s]) return pk_fail(PK_ERR_INVALID, "null tree in set");
+        int rc = pk_kcoal(sims[s], target, out + s);
+        if (rc) return rc;
+    }
     return PK_OK;
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cstddef>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -64,6 +65,12 @@ size_t pk_rowpart_bytes(const pk_tree &t, int precision);
 size_t pk_colpart_bytes(const pk_tree &t, int precision);
 void pk_rowpart_pack(const pk_tree &t, int precision, unsigned char *dst);
 void pk_colpart_pack(const pk_tree &t, int precision, unsigned char *dst);
+
+// runs fn(worker) on `workers` threads (the caller is worker 0, the rest come from a process-wide pool of parked
+// threads: starting a std::thread per call costs more than flattening a small batch of trees).  Fork-safe: a child
+// process builds its own pool on first use.
+void pk_parallel(int workers, const std::function<void(int)> &fn);
+int pk_host_threads();
 
 void pk_set_error(const std::string &msg);
 int pk_fail(int code, const std::string &msg);

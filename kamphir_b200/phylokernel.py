@@ -461,7 +461,8 @@ class PhyloKernel(object):
                                         k.ctypes.data, d.ctypes.data, kh.ctypes.data))
         res = dict(k=k, denom=d, knorm=kh, ref_denom=ref.value)
         if use_kcoal:
-            kc = np.array([t.kcoal(fo) for t in fs])
+            kc = np.empty(n)
+            check(_lib.lib().pk_kcoal_batch(arr, n, fo._h, kc.ctypes.data))
             res['kcoal'] = kc
             res['score'] = kh * np.power(kc, 1.0 if kadj is None else kadj)
             res['mean_score'] = float(res['score'].sum() / n)       # kamphir.py:450

@@ -162,3 +162,25 @@ def test_list_api_matches_single_calls():
             assert np.array_equal(x, y)
     with pytest.raises(ValueError):
         FlatTree.many_from_newick_list(nwk[:3] + ["((a:1,b:2,c:3):1,d:1);"], 3, "mean")
+
+
+def _child_flatten(seed):
+    """Runs in a forked child: the parent's pool threads do not exist here, the library must build its own."""
+    nwk = [synth.kingman_newick(60, seed * 100 + i) for i in range(40)]
+    flats = FlatTree.many_from_newick("\n".join(nwk), nthreads=4)
+    return [f.n_internal for f in flats]
+
+
+@pytest.mark.timeout(120)
+def test_worker_pool_survives_fork():
+    """kamphir.py:638 creates an mp.Pool at module scope and forks workers that call the kernel object: the flattener's
+    parked worker threads must not be assumed to exist in a forked child."""
+    import multiprocessing as mp
+    nwk = [synth.kingman_newick(60, i) for i in range(64)]
+    parent = FlatTree.many_from_newick("\n".join(nwk), nthreads=4)        # pool threads now exist in this process
+    assert len(parent) == 64
+    with mp.get_context("fork").Pool(2) as pool:
+        out = pool.map(_child_flatten, [1, 2, 3])
+    assert all(x == [59] * 40 for x in out)
+    again = FlatTree.many_from_newick("\n".join(nwk), nthreads=4)         # and the parent's pool still works
+    assert [f.n_internal for f in again] == [59] * 64
