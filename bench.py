@@ -221,7 +221,10 @@ def run_ours(args):
                          % (args.gpus, world, args.gpus))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("PK_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # stdout carries the one JSON line: NCCL's own messages (it prints its version at WARN and above) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if "PK_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["PK_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     t0 = time.perf_counter()
