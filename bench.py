@@ -219,10 +219,14 @@ def run_ours(args):
     if world != args.gpus:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run --nproc-per-node %d"
                          % (args.gpus, world, args.gpus))
+    # stdout carries the one JSON line and nothing else: libraries that write to file descriptor 1 themselves (NCCL prints
+    # its version there whenever NCCL_DEBUG is set in the environment) are pointed at stderr, the line goes to a private
+    # duplicate of the original stdout
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout carries the one JSON line: NCCL's own messages (it prints its version at WARN and above) go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if "PK_NCCL_DEBUG" in os.environ:
             os.environ["NCCL_DEBUG"] = os.environ["PK_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -389,7 +393,7 @@ def run_ours(args):
                         "Python 2.7 + Biopython are absent from the image" % sys.version.split()[0],
                 "c_restatement_pair_evals_per_s": c_rate2, "port_vs_c_max_rel_diff": port_err,
                 "host_cores_available": os.cpu_count()}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     barrier()
     runner.close()
     if world > 1:
