@@ -182,9 +182,10 @@ struct __align__(16) LevelDesc {
     int rows;       // rows at this level in this class (0: empty, skipped)
     int wB;         // columns = nodes of the column tree in this class
     int colbase;    // first column (kernel order in the column tree)
-    int cbase;      // unused (rows carry their own C offsets)
+    int chunk_end;  // DEAL: the level's 32-column chunks are numbered across its rectangles, this one owns [chunk_end - n, chunk_end)
     int flags;      // bit 8: last rectangle of its level (a barrier follows); bit 9 / 10: slot 0 / 1 always a tip
-    int pad0, pad1;
+    int nchunks;    // DEAL, in the level's first descriptor: chunks of the whole level
+    int pad1;
 };
 #ifndef PK_DESC_MAX
 #define PK_DESC_MAX 48
@@ -238,7 +239,7 @@ __device__ __forceinline__ int4 lds_int4(const int4 *p) {     // always one LDS.
 // child cell of slot 0 / 1: the stored cell when the children's classes agree, else cell 1 (= 1, productions differ)
 #define PK_GATHER0(q) C.ld((((q).w ^ qb0) & 0xff) == 0 ? (q).x + kb0 : 1)
 #define PK_GATHER1(q) C.ld((((q).w ^ qb1) & 0xff00) == 0 ? (q).y + kb1 : 1)
-template <typename T, bool CSMEM, bool G0, bool G1, int U>
+template <typename T, bool CSMEM, bool G0, bool G1, int U, bool FENCE>
 __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0, T b1, int cb0, int cb1, int pkey,
                                      const Cells<T, CSMEM> &C, const GaussK<T> &gk, T sigma, T tipf) {
     const int qb0 = (unsigned)cb0 >> 24, kb0 = cb0 & 0xffffff;             // child class + 1 (0 = tip), rank in its group
@@ -274,6 +275,10 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
                 if (G0) f0[u] = PK_GATHER0(q);
                 if (G1) f1[u] = PK_GATHER1(q);
             }
+            // ptxas is free to sink the gathers below the Gaussians, and whether it does depends on unrelated code around
+            // the loop (375 instead of 445 Gcells/s when the chunk-dealing level loop was introduced).  Memory operations
+            // do not cross a warp barrier: FENCE pins the gathers here (413; costs 2 % where ptxas behaves by itself).
+            if (FENCE) __syncwarp(__activemask());
         }
         pk_gauss<U>(x, ev, gk);
 #pragma unroll
@@ -330,7 +335,9 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
 // therefore walks the same rows of a (level, class) rectangle -- no work splitting, no per-warp bookkeeping, perfectly
 // balanced level barriers -- and a CTA has as many warps as the widest class needs (6 for 500-tip trees), several CTAs
 // (pairs) being resident per SM.
-template <typename T, bool CSMEM, int BOUND>     // BOUND: upper bound of the CTA size (sets the register budget)
+// DEAL: the 32-column chunks of all rectangles of a level are dealt to the warps (labelled trees: many narrow classes);
+// otherwise thread t owns column t of every rectangle and the rectangles of a level run one after the other.
+template <typename T, bool CSMEM, int BOUND, bool DEAL>     // BOUND: upper bound of the CTA size (sets the register budget)
 #ifndef PK_MINB192
 #define PK_MINB192 4
 #endif
@@ -495,21 +502,68 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 192 ? PK_MINB192 : BOUND <= 2
             __syncthreads();                       // previous batch done with s_desc; rowrec / s_coff visible
             for (int L = L0 + tid; L < L1; L += NT) {          // one thread per level describes its rectangles
                 LevelDesc *dst = s_desc + (L - L0) * ncls;
-                int last = -1;
+                int last = -1, chunks = 0;
                 for (int c = 0; c < ncls; ++c) {
                     const int r0 = lvlA[c * (nlevA + 1) + L], rows = lvlA[c * (nlevA + 1) + L + 1] - r0, wB = s_cntB[c];
                     LevelDesc d;
-                    d.r0 = r0; d.rows = 0; d.wB = wB; d.colbase = clsB[c]; d.cbase = 0; d.flags = 0; d.pad0 = d.pad1 = 0;
+                    d.r0 = r0; d.rows = 0; d.wB = wB; d.colbase = clsB[c]; d.flags = 0; d.nchunks = 0; d.pad1 = 0;
                     if (rows > 0 && wB > 0) {
                         d.rows = rows;
                         d.flags = (((tip0mask >> c) & 1ull) ? 512 : 0) | (((tip1mask >> c) & 1ull) ? 1024 : 0);
                         last = c;
+                        chunks += (wB + 31) >> 5;
                     }
+                    d.chunk_end = chunks;
                     dst[c] = d;
                 }
                 if (last >= 0) dst[last].flags |= 256;
+                dst[0].nchunks = chunks;
             }
             __syncthreads();
+#define PK_COLUMN(D, JB)                                                                                              \
+    {                                                                                                                 \
+        const int col = (D).colbase + (JB);                                                                           \
+        const T b0 = b0p[col], b1 = b1p[col];                                                                         \
+        const int pkey = pcB[col] << 16;                  /* this column's parent code, aligned with rec.packed */   \
+        const RowRec<T> *rp = rowrec + (D).r0;                                                                        \
+        T part;                                                                                                       \
+        switch ((D).flags & (512 | 1024)) {               /* bit 9 / 10: slot 0 / 1 is a tip in every row of the class */ \
+        case 512 | 1024:                                                                                              \
+            part = pk_rect<T, CSMEM, false, false, U, DEAL>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,   \
+                                                            cells, gk, sigma, tipf);                                  \
+            break;                                                                                                    \
+        case 512:                                                                                                     \
+            part = pk_rect<T, CSMEM, false, true, U, DEAL>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,    \
+                                                           cells, gk, sigma, tipf);                                   \
+            break;                                                                                                    \
+        case 1024:                                                                                                    \
+            part = pk_rect<T, CSMEM, true, false, U, DEAL>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,    \
+                                                           cells, gk, sigma, tipf);                                   \
+            break;                                                                                                    \
+        default:                                                                                                      \
+            part = pk_rect<T, CSMEM, true, true, U, DEAL>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,     \
+                                                          cells, gk, sigma, tipf);                                    \
+        }                                                                                                             \
+        acc += (double)part;                                                                                          \
+    }
+            if (DEAL) {
+                // The rectangles of a level are independent: their 32-column chunks are numbered through and dealt to the
+                // warps round-robin, so a level of several narrow rectangles (1 + 2S + S^2 classes with S tip states)
+                // keeps all warps busy instead of running the rectangles one after the other on a few warps each.
+                for (int lv = 0; lv < L1 - L0; ++lv) {
+                    const LevelDesc *dl = s_desc + lv * ncls;
+                    const int nchunks = dl[0].nchunks;
+                    for (int ch = warp; ch < nchunks; ch += NW) {
+                        int e = 0;
+                        while (ch >= dl[e].chunk_end) ++e;             // uniform per warp, at most ncls steps
+                        const LevelDesc d = dl[e];
+                        const int jb = ((ch - (d.chunk_end - ((d.wB + 31) >> 5))) << 5) + lane;
+                        if (jb < d.wB) PK_COLUMN(d, jb)
+                    }
+                    if (nchunks > 0) __syncthreads();    // end of a level: its cells are final before the next one reads
+                }
+                continue;
+            }
             const int ndesc = (L1 - L0) * ncls;
             for (int e = 0; e < ndesc; ++e) {
                 const LevelDesc d = s_desc[e];
@@ -517,34 +571,11 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 192 ? PK_MINB192 : BOUND <= 2
                 const int wB = d.wB;
                 // thread t owns column t; a rectangle wider than the CTA (rare: the CTA is sized for the bulk of the
                 // trees, not the widest) is finished by the first threads taking a second column
-                for (int jb = tid; jb < wB; jb += NT) {
-                    const int col = d.colbase + jb;
-                    const T b0 = b0p[col], b1 = b1p[col];
-                    const int pkey = pcB[col] << 16;              // this column's parent code, aligned with rec.packed
-                    const RowRec<T> *rp = rowrec + d.r0;
-                    T part;
-                    switch (d.flags & (512 | 1024)) {             // bit 9 / 10: slot 0 / 1 is a tip in every row of the class
-                    case 512 | 1024:
-                        part = pk_rect<T, CSMEM, false, false, U>(rp, d.rows, jb, b0, b1, codeB0[col], codeB1[col], pkey, cells,
-                                                                  gk, sigma, tipf);
-                        break;
-                    case 512:
-                        part = pk_rect<T, CSMEM, false, true, U>(rp, d.rows, jb, b0, b1, codeB0[col], codeB1[col], pkey, cells,
-                                                                 gk, sigma, tipf);
-                        break;
-                    case 1024:
-                        part = pk_rect<T, CSMEM, true, false, U>(rp, d.rows, jb, b0, b1, codeB0[col], codeB1[col], pkey, cells,
-                                                                 gk, sigma, tipf);
-                        break;
-                    default:
-                        part = pk_rect<T, CSMEM, true, true, U>(rp, d.rows, jb, b0, b1, codeB0[col], codeB1[col], pkey, cells,
-                                                                gk, sigma, tipf);
-                    }
-                    acc += (double)part;
-                }
+                for (int jb = tid; jb < wB; jb += NT) PK_COLUMN(d, jb)
                 if (d.flags & 256) __syncthreads();      // end of a level: its cells are final before the next one reads
             }
         }
+#undef PK_COLUMN
 
         // ---- deterministic block reduction of K ---------------------------------------------------
 #pragma unroll
@@ -972,50 +1003,54 @@ extern "C" int pk_forest_pair_stats(const pk_forest *fa, const pk_forest *fb, co
 // ---------------------------------------------------------------------------------------------------
 // The dynamic shared-memory limit of a kernel variant is raised once per size and its occupancy is queried once per
 // (CTA size, shared memory): a sim-vs-obs proposal is one 30 us launch, the driver calls would cost more than that.
-template <typename T, bool CSMEM, int BOUND>
+template <typename T, bool CSMEM, int BOUND, bool DEAL>
 static cudaError_t launch_t(pk_ctx *ctx, const DpArgs &args, int grid, int nt, int smem, cudaStream_t stream) {
-    int &have = ctx->attr_smem[{(int)sizeof(T), (int)CSMEM, BOUND}];
+    int &have = ctx->attr_smem[{(int)sizeof(T) + 16 * (int)DEAL, (int)CSMEM, BOUND}];
     if (smem > have) {
-        cudaError_t e = cudaFuncSetAttribute(pk_dp_kernel<T, CSMEM, BOUND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e =
+            cudaFuncSetAttribute(pk_dp_kernel<T, CSMEM, BOUND, DEAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         have = smem;
     }
-    pk_dp_kernel<T, CSMEM, BOUND><<<grid, nt, smem, stream>>>(args);
+    pk_dp_kernel<T, CSMEM, BOUND, DEAL><<<grid, nt, smem, stream>>>(args);
     return cudaGetLastError();
 }
 
-template <typename T, bool CSMEM, int BOUND>
+template <typename T, bool CSMEM, int BOUND, bool DEAL>
 static cudaError_t occupancy_t(pk_ctx *ctx, int nt, int smem, int *blocks) {
-    auto key = std::make_tuple((int)sizeof(T), (int)CSMEM, BOUND, nt, smem);
+    auto key = std::make_tuple((int)sizeof(T) + 16 * (int)DEAL, (int)CSMEM, BOUND, nt, smem);
     auto it = ctx->occupancy.find(key);
     if (it != ctx->occupancy.end()) {
         *blocks = it->second;
         return cudaSuccess;
     }
-    int &have = ctx->attr_smem[{(int)sizeof(T), (int)CSMEM, BOUND}];
+    int &have = ctx->attr_smem[{(int)sizeof(T) + 16 * (int)DEAL, (int)CSMEM, BOUND}];
     if (smem > have) {
-        cudaError_t e = cudaFuncSetAttribute(pk_dp_kernel<T, CSMEM, BOUND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e =
+            cudaFuncSetAttribute(pk_dp_kernel<T, CSMEM, BOUND, DEAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         have = smem;
     }
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, pk_dp_kernel<T, CSMEM, BOUND>, nt, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, pk_dp_kernel<T, CSMEM, BOUND, DEAL>, nt, smem);
     if (e == cudaSuccess) ctx->occupancy[key] = *blocks;
     return e;
 }
 
 // register budgets: <= 224 threads: 72 registers (4 CTAs of 7 warps per SM), <= 256: 80 (3 CTAs), <= 384: 80 (2 CTAs),
 // <= 512: 128, <= 768: 80, else 64 (one CTA per SM)
-#define PK_DISPATCH_NT(FN, TT, CS, ...)                                                         \
-    (nt <= 192   ? FN<TT, CS, 192>(__VA_ARGS__)                                                 \
-     : nt <= 224 ? FN<TT, CS, 224>(__VA_ARGS__)                                                 \
-     : nt <= 256 ? FN<TT, CS, 256>(__VA_ARGS__)                                                 \
-     : nt <= 384 ? FN<TT, CS, 384>(__VA_ARGS__)                                                 \
-     : nt <= 512 ? FN<TT, CS, 512>(__VA_ARGS__)                                                 \
-     : nt <= 768 ? FN<TT, CS, 768>(__VA_ARGS__)                                                 \
-                 : FN<TT, CS, 1024>(__VA_ARGS__))
-#define PK_DISPATCH(FN, ...)                                                                    \
-    (prec32 ? (csmem ? PK_DISPATCH_NT(FN, float, true, __VA_ARGS__) : PK_DISPATCH_NT(FN, float, false, __VA_ARGS__)) \
-            : (csmem ? PK_DISPATCH_NT(FN, double, true, __VA_ARGS__) : PK_DISPATCH_NT(FN, double, false, __VA_ARGS__)))
+#define PK_DISPATCH_NT(FN, TT, CS, DL, ...)                                                     \
+    (nt <= 192   ? FN<TT, CS, 192, DL>(__VA_ARGS__)                                             \
+     : nt <= 224 ? FN<TT, CS, 224, DL>(__VA_ARGS__)                                             \
+     : nt <= 256 ? FN<TT, CS, 256, DL>(__VA_ARGS__)                                             \
+     : nt <= 384 ? FN<TT, CS, 384, DL>(__VA_ARGS__)                                             \
+     : nt <= 512 ? FN<TT, CS, 512, DL>(__VA_ARGS__)                                             \
+     : nt <= 768 ? FN<TT, CS, 768, DL>(__VA_ARGS__)                                             \
+                 : FN<TT, CS, 1024, DL>(__VA_ARGS__))
+#define PK_DISPATCH_CS(FN, TT, DL, ...) \
+    (csmem ? PK_DISPATCH_NT(FN, TT, true, DL, __VA_ARGS__) : PK_DISPATCH_NT(FN, TT, false, DL, __VA_ARGS__))
+#define PK_DISPATCH(FN, ...)                                                                                \
+    (prec32 ? (deal ? PK_DISPATCH_CS(FN, float, true, __VA_ARGS__) : PK_DISPATCH_CS(FN, float, false, __VA_ARGS__)) \
+            : (deal ? PK_DISPATCH_CS(FN, double, true, __VA_ARGS__) : PK_DISPATCH_CS(FN, double, false, __VA_ARGS__)))
 
 static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpArgs args, const pk_params *p) {
     if (fa->ctx != ctx || fb->ctx != ctx) return pk_fail(PK_ERR_INVALID, "forest belongs to another context");
@@ -1027,6 +1062,7 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
         return pk_fail(PK_ERR_INVALID, "decayFactor, gaussFactor, sigma must be finite and gaussFactor non-zero");
     if (args.total <= 0) return PK_OK;
     const bool prec32 = fa->precision == 32;
+    const bool deal = fa->ncls > 3;      // labelled trees: many narrow class rectangles per level, dealt to the warps by chunks
     const size_t w = prec32 ? 4 : 8;
 
     args.blocksA = fa->d_blocks;

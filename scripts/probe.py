@@ -15,9 +15,10 @@ def main():
     tips = int(sys.argv[2]) if len(sys.argv) > 2 else 500
     prec_list = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [64, 32]
     cfgs = sys.argv[4] if len(sys.argv) > 4 else "0:0:0,512:1:1,512:2:1,1024:1:1,256:2:1,256:4:1"
+    states = int(sys.argv[5]) if len(sys.argv) > 5 else 0      # tip states (BASELINE.json configs[2]): labelled productions
     t0 = time.time()
-    nwk = synth.tree_set(n, tips, 3000, "mixed")
-    flats = FlatTree.many_from_newick("\n".join(nwk))
+    nwk = synth.tree_set(n, tips, 3000, "mixed", states, [1.0 / states] * states if states else None)
+    flats = FlatTree.many_from_newick("\n".join(nwk), 3, "mean", states)
     print("gen+flatten %.2fs" % (time.time() - t0), flush=True)
     ctx = get_context(0)
     L = _lib.lib()
