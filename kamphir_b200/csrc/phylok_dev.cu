@@ -188,8 +188,9 @@ struct __align__(16) LevelDesc {
     int pad1;
 };
 #ifndef PK_DESC_MAX
-#define PK_DESC_MAX 48
+#define PK_DESC_MAX 64
 #endif
+static_assert(PK_DESC_MAX >= PK_MAX_CLASSES, "one level's descriptors (one per class) must fit the descriptor buffer");
 
 // ---------------------------------------------------------------------------------------------------
 // stored C cells of one pair: a shared-memory array (tiny trees) or this CTA's slab in HBM.  The slab base is an opaque

@@ -306,6 +306,22 @@ def test_labelled_tip_states_against_extension_oracle():
     assert rel(lab, plain) < 1e-13
 
 
+@pytest.mark.parametrize("S", [3, 7])
+def test_labelled_many_classes(S):
+    """Up to 1 + 2S + S^2 = 64 production classes (S = 7): narrow class rectangles dealt to the warps by chunks, one
+    descriptor per class and level; Gram form and pair form agree with the extension oracle."""
+    nwk = [synth.kingman_newick(150, 900 + i, states=S) for i in range(3)] + [synth.yule_newick(260, 950, states=S)]
+    flats = [FlatTree.from_newick(s, 3, "mean", S) for s in nwk]
+    of = [po.prep_kamphir(po.read_newick(s), "mean", po.state_from_name) for s in nwk]
+    want = np.array([[po.kernel_arrays_labelled(a, b, 0.2, 2.0) for b in of] for a in of])
+    for precision in (64, 32):
+        pk = PhyloKernel(n_states=S, precision=precision, **KAM)
+        got = pk.kernel_batch(flats)
+        assert rel(got, want) <= TOL[precision]
+        raw = pk.gram(flats, normalised=False)
+        assert rel(raw, want) <= TOL[precision]
+
+
 def test_load_trees_from_file_and_compute_matrix(tmp_path):
     """The reference's broken matrix surface (phyloK2.py:68-99,148-156) works here."""
     nwk = synth.tree_set(5, 30, 10)
