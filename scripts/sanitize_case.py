@@ -17,4 +17,13 @@ for prec in (64, 32):
     g = pk.gram(flats, normalised=True)
     assert np.allclose(np.diag(g), 1.0)
     r = pk.score_batch(flats[6], flats[:6])
+    # labelled trees (chunk-dealing kernel variant), a CTA narrower than the rectangles (second chunk per warp), lambda = 0
+    lab = [FlatTree.from_newick(synth.kingman_newick(90, 40 + i, states=3), 3, "mean", 3) for i in range(4)]
+    kl = PhyloKernel(decayFactor=0.2, gaussFactor=2.0, precision=prec, n_states=3).kernel_batch(lab)
+    assert np.all(np.isfinite(kl))
+    get_context().configure(64, 0, 0)
+    k2 = pk.kernel_batch(flats[5:])
+    assert np.all(np.isfinite(k2))
+    get_context().configure(0, 0, 0)
+    assert np.all(PhyloKernel(decayFactor=0.0, precision=prec).kernel_batch(flats[:4]) == 0.0)
 print("sanitize case ok")
