@@ -197,11 +197,27 @@ static_assert(PK_DESC_MAX >= PK_MAX_CLASSES, "one level's descriptors (one per c
 // 64-bit value in a vector register pair, so every cell address is one IMAD.WIDE with an immediate 8 (or 4); the accesses
 // are explicit ld.global / st.global (the opaque base would otherwise decay to generic LD/ST).
 // ---------------------------------------------------------------------------------------------------
+// -DPK_DEBUG_BOUNDS (scripts/bounds_check.sh; compute-sanitizer is not available on the GPU pool): every cell index is
+// checked against the slab / shared-memory array size, violations are counted and the launch fails.
 template <typename T, bool CSMEM>
 struct Cells {
     T *sm;
     unsigned long long base;
+#ifdef PK_DEBUG_BOUNDS
+    unsigned limit;
+    unsigned long long *err;
+    __device__ __forceinline__ int chk(int idx) const {
+        if ((unsigned)idx >= limit) {
+            atomicAdd(err, 1ull);
+            return 0;
+        }
+        return idx;
+    }
+#else
+    __device__ __forceinline__ int chk(int idx) const { return idx; }
+#endif
     __device__ __forceinline__ T ld(int idx) const {
+        idx = chk(idx);
         if (CSMEM) return sm[idx];
         T v;
         const unsigned long long addr = base + (unsigned long long)(unsigned)idx * sizeof(T);
@@ -210,6 +226,7 @@ struct Cells {
         return v;
     }
     __device__ __forceinline__ void st(int idx, T v) const {
+        idx = chk(idx);
         if (CSMEM) {
             sm[idx] = v;
             return;
@@ -367,6 +384,10 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 192 ? PK_MINB192 : BOUND <= 2
     Cells<T, CSMEM> cells;
     cells.sm = reinterpret_cast<T *>(smem + info_at + a.rowinfo_bytes);
     cells.base = (unsigned long long)(reinterpret_cast<T *>(a.scratch) + slab_off);
+#ifdef PK_DEBUG_BOUNDS
+    cells.limit = (unsigned)a.slab_elems;
+    cells.err = a.counter + 1;
+#endif
     if (tid == 0) mbar_init(&s_bar, 1);
     if (sizeof(T) == 8)
         for (int i = tid; i < PK_EXP_TAB * PK_EXP_REP; i += NT) s_tab[i] = a.exp_tab[i / PK_EXP_REP];
@@ -1173,12 +1194,26 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
         if (rc) return rc;
         args.scratch = ctx->d_scratch;
     }
+#ifdef PK_DEBUG_BOUNDS
+    if (csmem) args.slab_elems = c_bytes / (long long)w;                      // the limit the cell indices are checked against
+    args.counter = ctx->d_counters + 2 * (ctx->counter_next++ % (kCounterRing / 2));   // [work counter, violations]
+    PK_CUDA(cudaMemsetAsync(args.counter, 0, 2 * sizeof(unsigned long long), ctx->stream));
+#else
     args.counter = ctx->d_counters + (ctx->counter_next++ % kCounterRing);
     PK_CUDA(cudaMemsetAsync(args.counter, 0, sizeof(unsigned long long), ctx->stream));
+#endif
     PK_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     e = PK_DISPATCH(launch_t, ctx, args, grid, nt, smem, ctx->stream);
     if (e != cudaSuccess) return pk_fail(PK_ERR_CUDA, std::string("DP kernel launch: ") + cudaGetErrorString(e));
     PK_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+#ifdef PK_DEBUG_BOUNDS
+    {
+        unsigned long long bad = 0;
+        PK_CUDA(cudaMemcpyAsync(&bad, args.counter + 1, sizeof(bad), cudaMemcpyDeviceToHost, ctx->stream));
+        PK_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (bad) return pk_fail(PK_ERR_CUDA, "PK_DEBUG_BOUNDS: " + std::to_string(bad) + " cell accesses outside the C storage");
+    }
+#endif
     ctx->ev_valid = true;
     ctx->launches++;
     ctx->last_path = csmem ? 0 : 1;
