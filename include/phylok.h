@@ -139,6 +139,15 @@ int pk_forest_kernel_pairs(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb
 int pk_score_batch(pk_ctx *ctx, const pk_tree *obs, const pk_tree *const *sims, int32_t nsims, const pk_params *params,
                    double *ref_denom, double *out_k, double *out_denom, double *out_khat);
 
+/* One ABC proposal in one call, from the simulators' Newick strings (kamphir.py:318 hands them over as text) to the
+ * scores of kamphir.py:288-306 and their mean (:450): parse + prep (prep_flags / normalize / n_states as in
+ * pk_trees_from_newick_list) on the worker pool, one DP launch (pk_score_batch), kcoal (unless kadj is NaN) and
+ * score[s] = khat[s] * kcoal[s]^kadj.  obs is the target tree, flattened once per run.  Any output may be NULL. */
+int pk_score_newick_batch(pk_ctx *ctx, const pk_tree *obs, const char *const *sims, const size_t *lens, int32_t nsims,
+                          int prep_flags, int normalize, int n_states, int nthreads, const pk_params *params,
+                          double *ref_denom, double kadj, double *out_k, double *out_denom, double *out_khat,
+                          double *out_kcoal, double *out_score, double *out_mean);
+
 /* All-pairs Gram matrix, the working form of PhyloKernel.compute_matrix (phyloK2.py:148-156): out is N x N row-major,
  * symmetric; normalised = 0: raw K (reference semantics); 1: K / sqrt(K_ii K_jj).  Host-resident form. */
 int pk_gram(pk_ctx *ctx, const pk_tree *const *trees, int32_t n, const pk_params *params, int normalised, double *out);

@@ -58,6 +58,9 @@ SIGNATURES = {
     "pk_forest_gram_stats": (ctypes.c_int, [_P, _I32, _I32, _I32, _P]),
     "pk_kernel_pairs": (ctypes.c_int, [_P, _P, _I32, _P, _I32, _P, _I32, ctypes.POINTER(pk_params), _P]),
     "pk_forest_kernel_pairs": (ctypes.c_int, [_P, _P, _P, _P, _I32, ctypes.POINTER(pk_params), _P]),
+    "pk_score_newick_batch": (ctypes.c_int, [_P, _P, _P, _P, _I32, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.POINTER(pk_params), ctypes.POINTER(_D), _D, _P, _P, _P, _P, _P,
+                                             ctypes.POINTER(_D)]),
     "pk_score_batch": (ctypes.c_int, [_P, _P, _P, _I32, ctypes.POINTER(pk_params), ctypes.POINTER(_D), _P, _P, _P]),
     "pk_gram": (ctypes.c_int, [_P, _P, _I32, ctypes.POINTER(pk_params), ctypes.c_int, _P]),
     "pk_forest_gram_part": (ctypes.c_int, [_P, _P, ctypes.POINTER(pk_params), ctypes.c_int, _I32, _I32, _I32, _P, _I64, _P]),

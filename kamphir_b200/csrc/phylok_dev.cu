@@ -25,6 +25,7 @@
 #include <cstdio>
 #include <cstring>
 #include <atomic>
+#include <limits>
 #include <map>
 #include <string>
 #include <thread>
@@ -1314,6 +1315,42 @@ extern "C" int pk_score_batch(pk_ctx *ctx, const pk_tree *obs, const pk_tree *co
             out_khat[s] = std::exp(std::log(k[s]) - 0.5 * (std::log(*ref_denom) + std::log(k[(size_t)nsims + s])));
     }
     return PK_OK;
+}
+
+extern "C" int pk_score_newick_batch(pk_ctx *ctx, const pk_tree *obs, const char *const *sims, const size_t *lens,
+                                     int32_t nsims, int prep_flags, int normalize, int n_states, int nthreads,
+                                     const pk_params *params, double *ref_denom, double kadj, double *out_k,
+                                     double *out_denom, double *out_khat, double *out_kcoal, double *out_score,
+                                     double *out_mean) {
+    if (!ctx || !obs || !sims || !lens || !params || !ref_denom) return pk_fail(PK_ERR_INVALID, "null argument");
+    if (nsims < 1) return pk_fail(PK_ERR_INVALID, "no simulated trees");
+    pk_tree **trees = nullptr;
+    int32_t n = 0;
+    int rc = pk_trees_from_newick_list(sims, lens, nsims, prep_flags, normalize, n_states, nthreads, &trees, &n);
+    if (rc) return rc;
+    std::vector<double> khat((size_t)n), kc;
+    rc = pk_score_batch(ctx, obs, trees, n, params, ref_denom, out_k, out_denom, khat.data());
+    const bool use_kcoal = !std::isnan(kadj);
+    if (rc == PK_OK && use_kcoal) {
+        kc.resize((size_t)n);
+        rc = pk_kcoal_batch(trees, n, obs, kc.data());
+    }
+    if (rc == PK_OK) {
+        double sum = 0.0;
+        for (int32_t s = 0; s < n; ++s) {
+            const double score = use_kcoal ? khat[s] * std::pow(kc[s], kadj) : khat[s];      // kamphir.py:306
+            if (out_khat) out_khat[s] = khat[s];
+            if (out_kcoal) out_kcoal[s] = use_kcoal ? kc[s] : std::numeric_limits<double>::quiet_NaN();
+            if (out_score) out_score[s] = score;
+            sum += score;
+        }
+        if (out_mean) *out_mean = sum / n;                                                   // kamphir.py:450
+    }
+    std::string keep = rc ? std::string(pk_last_error()) : std::string();
+    for (int32_t s = 0; s < n; ++s) pk_tree_free(trees[s]);
+    pk_tree_array_free(trees);
+    if (rc) pk_set_error(keep);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------

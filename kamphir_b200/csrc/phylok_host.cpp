@@ -384,8 +384,7 @@ int flatten(const char *text, Scratch &sc, int flags, int normalize, int nstates
         out.heights.reserve((size_t)total / 2 + 1);
         for (int32_t v : pre)
             if (nd[v].first >= 0) out.heights.push_back(hmax - depth[v]);
-        std::sort(out.heights.begin(), out.heights.end());   // here, on the worker: kamphir's compute() always uses kcoal
-        out.heights_sorted = true;
+        out.heights_sorted = false;    // sorted on first use: pk_kcoal_batch spreads that over the worker pool
     }
 
     // normalize_tree (phyloK2.py:101-130): every non-root branch divided by the mean / median
@@ -963,10 +962,31 @@ extern "C" int pk_kcoal(const pk_tree *sim, const pk_tree *target, double *out) 
 
 extern "C" int pk_kcoal_batch(const pk_tree *const *sims, int32_t nsims, const pk_tree *target, double *out) {
     if (!sims || !target || (nsims > 0 && !out)) return pk_fail(PK_ERR_INVALID, "null argument");
-    for (int32_t s = 0; s < nsims; ++s) {
+    for (int32_t s = 0; s < nsims; ++s)
         if (!sims[s]) return pk_fail(PK_ERR_INVALID, "null tree in set");
-        int rc = pk_kcoal(sims[s], target, out + s);
-        if (rc) return rc;
-    }
+    // the replicates' node heights are sorted here, on first use (kamphir.py:257-258): one worker per ~64 k nodes
+    size_t nodes = 0;
+    for (int32_t s = 0; s < nsims; ++s) nodes += (size_t)sims[s]->n;
+    const int workers = (int)std::min<size_t>((size_t)pk_host_threads(), std::max<size_t>(1, nodes / 65536));
+    std::atomic<int32_t> next{0};
+    std::atomic<int> status{PK_OK};
+    std::string first_err;
+    std::mutex err_lock;
+    pk_sorted_heights(target);
+    pk_parallel(workers, [&](int) {
+        for (;;) {
+            const int32_t s = next.fetch_add(1);
+            if (s >= nsims) break;
+            int rc = pk_kcoal(sims[s], target, out + s);
+            if (rc) {
+                std::lock_guard<std::mutex> lk(err_lock);
+                if (status.load() == PK_OK) {
+                    first_err = std::string(pk_last_error());
+                    status.store(rc);
+                }
+            }
+        }
+    });
+    if (status.load() != PK_OK) return pk_fail(status.load(), "replicate: " + first_err);
     return PK_OK;
 }

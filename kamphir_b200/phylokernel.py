@@ -451,6 +451,28 @@ class PhyloKernel(object):
         ``kcoal`` and ``score = knorm * kcoal**kadj`` and their mean (``mean_score``).
         """
         fo = self.flatten(obs, PK_PREP_KAMPHIR, self.normalize)
+        sims = list(sims)
+        if sims and all(isinstance(t, (str, bytes)) for t in sims):
+            # Newick text straight from the simulators (kamphir.py:318): parse, prep, DP launch, kcoal and the scores in
+            # one library call -- no per-tree Python objects
+            raw = [t.encode("utf-8") if isinstance(t, str) else t for t in sims]
+            n = len(raw)
+            ptrs = (ctypes.c_char_p * n)(*raw)
+            lens = (ctypes.c_size_t * n)(*[len(b) for b in raw])
+            out = np.empty((5, n))
+            ref = ctypes.c_double(float('nan') if ref_denom is None else float(ref_denom))
+            mean = ctypes.c_double()
+            p = self._params()
+            check(_lib.lib().pk_score_newick_batch(
+                self._ctx()._h, fo._h, ptrs, lens, n, int(PK_PREP_KAMPHIR), PK_NORM[self.normalize], int(self.n_states), 0,
+                ctypes.byref(p), ctypes.byref(ref), (1.0 if kadj is None else float(kadj)) if use_kcoal else float('nan'),
+                out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data, out[3].ctypes.data, out[4].ctypes.data,
+                ctypes.byref(mean)))
+            res = dict(k=out[0], denom=out[1], knorm=out[2], ref_denom=ref.value, mean_score=mean.value)
+            if use_kcoal:
+                res['kcoal'] = out[3]
+                res['score'] = out[4]
+            return res
         fs = self.flatten_list(sims, PK_PREP_KAMPHIR, self.normalize)
         n = len(fs)
         k, d, kh = np.empty(n), np.empty(n), np.empty(n)

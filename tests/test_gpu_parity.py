@@ -219,6 +219,26 @@ def test_score_batch_matches_kamphir_compute():
     assert np.all(res["knorm"] > 0) and np.all(res["knorm"] <= 1 + 1e-12)
 
 
+def test_score_batch_text_path_equals_object_path():
+    """Newick text goes through pk_score_newick_batch (one call), flattened trees through pk_score_batch + pk_kcoal_batch:
+    same numbers, also for labelled trees and the median normalisation; a bad replicate raises."""
+    for S, norm in ((0, "mean"), (0, "median"), (2, "mean")):
+        obs = synth.kingman_newick(70, 5, states=S)
+        sims = [synth.kingman_newick(70, 300 + i, states=S) for i in range(9)]
+        pk = PhyloKernel(normalize=norm, n_states=S, **KAM)
+        a = pk.score_batch(obs, [x.encode() for x in sims], use_kcoal=True, kadj=0.7)
+        fl = [FlatTree.from_newick(x, 3, norm, S) for x in sims]
+        b = pk.score_batch(obs, fl, use_kcoal=True, kadj=0.7)
+        for key in ("k", "denom", "knorm", "kcoal"):
+            assert np.array_equal(a[key], b[key]), key
+        assert rel(a["score"], b["score"]) < 1e-14           # pow() of the C library vs numpy's
+        assert a["mean_score"] == pytest.approx(b["mean_score"], rel=1e-15) and a["ref_denom"] == b["ref_denom"]
+        c = pk.score_batch(obs, sims)                      # without kcoal: the mean is the mean of knorm
+        assert "score" not in c and c["mean_score"] == pytest.approx(float(np.mean(a["knorm"])), rel=1e-14)
+    with pytest.raises(ValueError):
+        PhyloKernel(**KAM).score_batch("(a:1,b:2);", ["(a:1,b:2);", "((a:1,b:2,c:3):1,d:1);"])
+
+
 @pytest.mark.parametrize("precision", [64, 32])
 def test_gram_matrix(precision):
     """configs[3] in miniature: symmetry, unit diagonal, entries against the oracle, raw == compute_matrix semantics."""
