@@ -492,6 +492,15 @@ class PhyloKernel(object):
             res['mean_score'] = float(kh.sum() / n)
         return res
 
+    def score_batch_sharded(self, obs, sims, rank, world, group=None, ref_denom=None, kadj=None, use_kcoal=False):
+        """score_batch over the ranks of a torch.distributed group (one process per GPU): rank r scores every
+        world-th replicate, one all-gather returns the full result to every rank (kamphir_b200/score.py)."""
+        import torch
+        from .score import sharded_scores
+        dev = torch.device("cuda", torch.cuda.current_device()) if torch.distributed.get_backend(group) == "nccl" else None
+        return sharded_scores(lambda part: self.score_batch(obs, part, ref_denom=ref_denom, kadj=kadj, use_kcoal=use_kcoal),
+                              sims, rank, world, group, dev)
+
     def gram(self, trees, normalised=True):
         """All-pairs matrix over ``trees`` (FlatTree / Newick / tree objects): raw K or K/sqrt(K_ii K_jj)."""
         ft = self.flatten_list(trees, PK_PREP_KAMPHIR, self.normalize)

@@ -78,3 +78,41 @@ def test_partition_counts_for_bench_shape():
         assert max(pairs) - min(pairs) <= tile * tile * 2      # round-robin over 8256 tiles: near-perfect balance
         tiles = np.concatenate([part_tiles(n, tile, r, world) for r in range(world)])
         assert len(tiles) == 128 * 129 // 2 and len({(int(a), int(b)) for a, b in tiles}) == len(tiles)
+
+
+def _score_worker(rank, world, port, n, result_dir):
+    import torch.distributed as dist
+    from kamphir_b200 import synth
+    from kamphir_b200.score import shard_indices, sharded_scores
+    from oracle import phylok_oracle as po
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    obs = synth.kingman_newick(20, 1)
+    sims = [synth.kingman_newick(20, 50 + i) for i in range(n)]
+
+    def score_fn(part):      # the oracle's restatement of kamphir.py:249-306 stands in for the CUDA path on this box
+        mean, scores = po.kamphir_evaluate(part, obs, decayFactor=0.2, gaussFactor=2.0, normalize="mean")
+        return dict(score=np.array(scores), knorm=np.array(scores) * 0.5, ref_denom=1.25)
+
+    res = sharded_scores(score_fn, sims, rank, world)
+    assert sorted(sum((shard_indices(n, r, world) for r in range(world)), [])) == list(range(n))
+    if rank == 1:            # every rank holds the full result
+        want_mean, want = po.kamphir_evaluate(sims, obs, decayFactor=0.2, gaussFactor=2.0, normalize="mean")
+        np.save(os.path.join(result_dir, "ok.npy"),
+                np.array([bool(np.array_equal(res["score"], np.array(want))), abs(res["mean_score"] - want_mean) < 1e-15,
+                          res["ref_denom"] == 1.25, bool(np.array_equal(res["knorm"], np.array(want) * 0.5)),
+                          "kcoal" not in res]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [7, 8, 1])
+def test_two_ranks_sharded_proposal_scores(tmp_path, n):
+    """SURVEY 8e, sim-vs-obs row: replicates dealt to the ranks, one all-gather, original order restored (odd counts and
+    a rank without work included)."""
+    import torch.multiprocessing as mp
+    mp.spawn(_score_worker, args=(2, _free_port(), n, str(tmp_path)), nprocs=2, join=True)
+    ok = np.load(tmp_path / "ok.npy")
+    assert ok.all(), ok
