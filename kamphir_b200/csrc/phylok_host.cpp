@@ -163,10 +163,78 @@ struct Scratch {
     std::string err;
 };
 
-inline bool is_punct(char c) {
-    return c == '(' || c == ')' || c == '[' || c == ']' || c == '\'' || c == ':' || c == ';' || c == ',';
+// character classes of the Newick tokenizer: 1 = punctuation, 2 = white space
+struct CharClass {
+    unsigned char t[256];
+    constexpr CharClass() : t() {
+        for (int i = 0; i < 256; ++i) t[i] = 0;
+        for (char c : {'(', ')', '[', ']', '\'', ':', ';', ','}) t[(unsigned char)c] = 1;
+        for (char c : {' ', '\t', '\n', '\r', '\f', '\v'}) t[(unsigned char)c] = 2;
+    }
+};
+constexpr CharClass kCls;
+inline bool is_punct(char c) { return kCls.t[(unsigned char)c] == 1; }
+inline bool is_space(char c) { return kCls.t[(unsigned char)c] == 2; }
+inline bool is_token_end(char c) { return kCls.t[(unsigned char)c] != 0; }
+
+// Branch lengths: digits[.digits][e[+-]digits] with at most 19 significant digits and a power of ten within 10^22 is
+// the exact case of Clinger's fast path -- the decimal mantissa fits a double exactly (< 2^53) and so does the power
+// of ten, so one correctly rounded multiplication or division gives the correctly rounded result, the same double
+// strtod / Python's float() produce.  Everything else (longer mantissas, huge exponents, inf, nan, hex) goes to
+// std::from_chars.
+inline bool parse_length(const char *p, const char *end, double &out) {
+    static const double kPow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                      1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+    const char *q = p;
+    bool neg = false;
+    if (q < end && *q == '-') { neg = true; ++q; }
+    uint64_t m = 0;
+    int digits = 0, frac = 0;
+    bool any = false;
+    while (q < end && (unsigned)(*q - '0') < 10u) {
+        if (m || *q != '0') { if (++digits > 19) goto slow; m = m * 10 + (unsigned)(*q - '0'); }
+        any = true;
+        ++q;
+    }
+    if (q < end && *q == '.') {
+        ++q;
+        while (q < end && (unsigned)(*q - '0') < 10u) {
+            if (m || *q != '0') { if (++digits > 19) goto slow; m = m * 10 + (unsigned)(*q - '0'); }
+            any = true;
+            ++frac;
+            ++q;
+        }
+    }
+    if (!any) goto slow;
+    {
+        int ex = 0;
+        if (q < end && (*q == 'e' || *q == 'E')) {
+            ++q;
+            bool eneg = false;
+            if (q < end && (*q == '+' || *q == '-')) { eneg = *q == '-'; ++q; }
+            if (q >= end || (unsigned)(*q - '0') >= 10u) goto slow;
+            while (q < end && (unsigned)(*q - '0') < 10u) {
+                ex = ex * 10 + (*q - '0');
+                if (ex > 10000) goto slow;
+                ++q;
+            }
+            if (eneg) ex = -ex;
+        }
+        if (q != end) goto slow;
+        ex -= frac;
+        if (m >= ((uint64_t)1 << 53) || ex < -22 || ex > 22) goto slow;
+        double v = (double)m;
+        v = ex < 0 ? v / kPow10[-ex] : v * kPow10[ex];
+        out = neg ? -v : v;
+        return true;
+    }
+slow:
+    double v = 0.0;
+    auto res = std::from_chars(p, end, v);
+    if (p == end || res.ec != std::errc() || res.ptr != end) return false;
+    out = v;
+    return true;
 }
-inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\f' || c == '\v'; }
 
 // One tree from text[b, e) (no terminating ';').  Same token semantics as Biopython's Newick parser:
 // children in input order, '[...]' comments dropped, quoted labels, a ',' at top level creates a new root.
@@ -204,12 +272,11 @@ int parse_one(const char *text, size_t b, size_t e, RawTree &t, std::string &err
             size_t j = i + 1;
             while (j < e && text[j] == ' ') ++j;
             size_t k = j;
-            while (k < e && !is_punct(text[k]) && !is_space(text[k])) ++k;
+            while (k < e && !is_token_end(text[k])) ++k;
             size_t s = j;
             if (s < k && text[s] == '+') ++s;
             double v = 0.0;
-            auto res = std::from_chars(text + s, text + k, v);
-            if (s == k || res.ec != std::errc() || res.ptr != text + k) {
+            if (s == k || !parse_length(text + s, text + k, v)) {
                 err = "Newick: bad branch length '" + std::string(text + j, k - j) + "'";
                 return PK_ERR_PARSE;
             }
@@ -234,7 +301,7 @@ int parse_one(const char *text, size_t b, size_t e, RawTree &t, std::string &err
             return PK_ERR_PARSE;
         } else {
             size_t k = i;
-            while (k < e && !is_punct(text[k]) && !is_space(text[k])) ++k;
+            while (k < e && !is_token_end(text[k])) ++k;
             t.nd[cur].name_off = (int32_t)(i - b);
             t.nd[cur].name_len = (int32_t)(k - i);
             i = k;
@@ -565,33 +632,36 @@ int pk_tree_finish(pk_tree &t) {
     // Within a (class, parent code) group the columns are ordered by the parent codes of their ancestors (parent first),
     // i.e. like their parents are ordered among the columns of the parents' class.  The child cells that 32 consecutive
     // columns gather from one stored row are then (almost) consecutive too: 3.6 sectors per gather instead of 6.8 at
-    // 500 tips.  Five ancestors are enough (measured: 3.9 sectors with 4, 3.6 with 6 or 40).
+    // 500 tips.  The own parent code plus those of four ancestors are enough (measured: 3.9 sectors with 4 keys, 3.6 with
+    // 6 or 40).
     t.colorder.assign(n, 0);
     t.krank.assign(n, 0);
     {
-        // counting sort into the (class, parent code) groups (stable in post-order), then each small group by the
-        // parent codes of the next four ancestors (ties keep the post-order)
-        std::vector<int32_t> fill(t.gstart.begin(), t.gstart.end() - 1);
-        for (int32_t i = 0; i < n; ++i) t.colorder[fill[(size_t)t.cls[i] * npc + t.pcode[i]]++] = i;
-        std::vector<std::pair<uint32_t, int32_t>> keys;
-        for (size_t g = 0; g + 1 < t.gstart.size(); ++g) {
-            const int32_t lo = t.gstart[g], hi = t.gstart[g + 1];
-            if (hi - lo > 1) {
-                keys.resize((size_t)(hi - lo));
-                for (int32_t c = lo; c < hi; ++c) {
-                    const int32_t i = t.colorder[c];
-                    uint32_t k = 0;
-                    int32_t v = parent[i];
-                    for (int d = 0; d < 4; ++d) {
-                        k = (k << 8) | (v >= 0 ? t.pcode[v] : 0);
-                        if (v >= 0) v = parent[v];
-                    }
-                    keys[(size_t)(c - lo)] = {k, i};
-                }
-                std::sort(keys.begin(), keys.end());
-                for (int32_t c = lo; c < hi; ++c) t.colorder[c] = keys[(size_t)(c - lo)].second;
+        // least-significant-key-first radix sort, every pass a stable counting sort over at most npc (or ncls * npc)
+        // buckets: parent code of the 4th, 3rd, 2nd ancestor, of the parent, then the (class, parent code) group; ties
+        // keep the post-order
+        std::vector<int32_t> cur(n), nxt(n), cnt;
+        for (int32_t i = 0; i < n; ++i) cur[i] = i;
+        std::vector<uint8_t> key(n);
+        for (int d = 3; d >= 0; --d) {
+            for (int32_t i = 0; i < n; ++i) {
+                int32_t v = parent[i];
+                for (int k = 0; k < d && v >= 0; ++k) v = parent[v];
+                key[i] = v >= 0 ? t.pcode[v] : 0;
             }
-            for (int32_t c = lo; c < hi; ++c) t.krank[t.colorder[c]] = c - lo;
+            cnt.assign((size_t)npc + 1, 0);
+            for (int32_t i = 0; i < n; ++i) cnt[key[i] + 1]++;
+            for (int k = 0; k < npc; ++k) cnt[k + 1] += cnt[k];
+            for (int32_t c = 0; c < n; ++c) nxt[cnt[key[cur[c]]]++] = cur[c];
+            cur.swap(nxt);
+        }
+        std::vector<int32_t> fill(t.gstart.begin(), t.gstart.end() - 1);
+        for (int32_t c = 0; c < n; ++c) {
+            const int32_t i = cur[c];
+            const size_t g = (size_t)t.cls[i] * npc + t.pcode[i];
+            const int32_t col = fill[g]++;
+            t.colorder[col] = i;
+            t.krank[i] = col - t.gstart[g];
         }
     }
     t.hist.assign((size_t)ncls * 2 * (ncls + 1), 0);
@@ -964,10 +1034,10 @@ extern "C" int pk_kcoal_batch(const pk_tree *const *sims, int32_t nsims, const p
     if (!sims || !target || (nsims > 0 && !out)) return pk_fail(PK_ERR_INVALID, "null argument");
     for (int32_t s = 0; s < nsims; ++s)
         if (!sims[s]) return pk_fail(PK_ERR_INVALID, "null tree in set");
-    // the replicates' node heights are sorted here, on first use (kamphir.py:257-258): one worker per ~64 k nodes
+    // the replicates' node heights are sorted here, on first use (kamphir.py:257-258): one worker per ~4 k nodes
     size_t nodes = 0;
     for (int32_t s = 0; s < nsims; ++s) nodes += (size_t)sims[s]->n;
-    const int workers = (int)std::min<size_t>((size_t)pk_host_threads(), std::max<size_t>(1, nodes / 65536));
+    const int workers = (int)std::min<size_t>((size_t)pk_host_threads(), std::max<size_t>(1, nodes / 4096));
     std::atomic<int32_t> next{0};
     std::atomic<int> status{PK_OK};
     std::string first_err;
