@@ -27,6 +27,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdlib>
+#include <functional>
 #include <limits>
 #include <map>
 #include <string>
@@ -1248,8 +1249,11 @@ extern "C" int pk_forest_kernel_pairs(pk_ctx *ctx, const pk_forest *fa, const pk
     return launch_dp(ctx, fa, fb, args, params);
 }
 
-extern "C" int pk_kernel_pairs(pk_ctx *ctx, const pk_tree *const *A, int32_t nA, const pk_tree *const *B, int32_t nB,
-                               const int32_t *pairs, int32_t npairs, const pk_params *params, double *out_k) {
+// `while_running`, if set, is called after the launch is queued and before the host waits for the results: host work
+// that does not depend on them (kcoal) overlaps the kernel
+static int kernel_pairs_impl(pk_ctx *ctx, const pk_tree *const *A, int32_t nA, const pk_tree *const *B, int32_t nB,
+                             const int32_t *pairs, int32_t npairs, const pk_params *params, double *out_k,
+                             const std::function<void()> *while_running) {
     if (!ctx || !A || !B || !params || (npairs > 0 && (!pairs || !out_k))) return pk_fail(PK_ERR_INVALID, "null argument");
     if (npairs <= 0) return PK_OK;
     for (int32_t p = 0; p < npairs; ++p)
@@ -1286,6 +1290,7 @@ extern "C" int pk_kernel_pairs(pk_ctx *ctx, const pk_tree *const *A, int32_t nA,
                                             reinterpret_cast<double *>(d + pb_al));
             if (rc == PK_OK) {
                 e = cudaMemcpyAsync(h + pb_al, d + pb_al, ob, cudaMemcpyDeviceToHost, ctx->stream);
+                if (while_running) (*while_running)();
                 if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
                 if (e != cudaSuccess) rc = pk_fail(PK_ERR_CUDA, std::string("pk_kernel_pairs: ") + cudaGetErrorString(e));
                 else std::memcpy(out_k, h + pb_al, ob);
@@ -1299,9 +1304,14 @@ extern "C" int pk_kernel_pairs(pk_ctx *ctx, const pk_tree *const *A, int32_t nA,
     return rc;
 }
 
-extern "C" int pk_score_batch(pk_ctx *ctx, const pk_tree *obs, const pk_tree *const *sims, int32_t nsims,
-                              const pk_params *params, double *ref_denom, double *out_k, double *out_denom,
-                              double *out_khat) {
+extern "C" int pk_kernel_pairs(pk_ctx *ctx, const pk_tree *const *A, int32_t nA, const pk_tree *const *B, int32_t nB,
+                               const int32_t *pairs, int32_t npairs, const pk_params *params, double *out_k) {
+    return kernel_pairs_impl(ctx, A, nA, B, nB, pairs, npairs, params, out_k, nullptr);
+}
+
+static int score_batch_impl(pk_ctx *ctx, const pk_tree *obs, const pk_tree *const *sims, int32_t nsims,
+                            const pk_params *params, double *ref_denom, double *out_k, double *out_denom,
+                            double *out_khat, const std::function<void()> *while_running) {
     if (!ctx || !obs || !sims || !params || !ref_denom) return pk_fail(PK_ERR_INVALID, "null argument");
     if (nsims < 1) return pk_fail(PK_ERR_INVALID, "no simulated trees");
     std::vector<const pk_tree *> all((size_t)nsims + 1);
@@ -1318,7 +1328,8 @@ extern "C" int pk_score_batch(pk_ctx *ctx, const pk_tree *obs, const pk_tree *co
     }
     if (need_ref) pairs[2 * (size_t)(2 * nsims)] = pairs[2 * (size_t)(2 * nsims) + 1] = 0;
     std::vector<double> k((size_t)np);
-    int rc = pk_kernel_pairs(ctx, all.data(), nsims + 1, all.data(), nsims + 1, pairs.data(), np, params, k.data());
+    int rc = kernel_pairs_impl(ctx, all.data(), nsims + 1, all.data(), nsims + 1, pairs.data(), np, params, k.data(),
+                               while_running);
     if (rc) return rc;
     if (need_ref) *ref_denom = k[2 * (size_t)nsims];
     for (int32_t s = 0; s < nsims; ++s) {
@@ -1328,6 +1339,12 @@ extern "C" int pk_score_batch(pk_ctx *ctx, const pk_tree *obs, const pk_tree *co
             out_khat[s] = std::exp(std::log(k[s]) - 0.5 * (std::log(*ref_denom) + std::log(k[(size_t)nsims + s])));
     }
     return PK_OK;
+}
+
+extern "C" int pk_score_batch(pk_ctx *ctx, const pk_tree *obs, const pk_tree *const *sims, int32_t nsims,
+                              const pk_params *params, double *ref_denom, double *out_k, double *out_denom,
+                              double *out_khat) {
+    return score_batch_impl(ctx, obs, sims, nsims, params, ref_denom, out_k, out_denom, out_khat, nullptr);
 }
 
 extern "C" int pk_score_newick_batch(pk_ctx *ctx, const pk_tree *obs, const char *const *sims, const size_t *lens,
@@ -1346,12 +1363,23 @@ extern "C" int pk_score_newick_batch(pk_ctx *ctx, const pk_tree *obs, const char
     if (rc) return rc;
     const double t1 = trace ? now() : 0.0;
     std::vector<double> khat((size_t)n), kc;
-    rc = pk_score_batch(ctx, obs, trees, n, params, ref_denom, out_k, out_denom, khat.data());
-    const double t2 = trace ? now() : 0.0;
     const bool use_kcoal = !std::isnan(kadj);
-    if (rc == PK_OK && use_kcoal) {
+    // kcoal is host work (sorting the replicates' node heights) that does not depend on the DP: it runs on the worker
+    // pool while the kernel does (after the forest is packed and uploaded, which uses the same pool)
+    int rc_kcoal = PK_OK;
+    std::string err_kcoal;
+    bool kcoal_done = false;
+    std::function<void()> overlap = [&]() {
         kc.resize((size_t)n);
-        rc = pk_kcoal_batch(trees, n, obs, kc.data());
+        rc_kcoal = pk_kcoal_batch(trees, n, obs, kc.data());
+        if (rc_kcoal) err_kcoal = pk_last_error();
+        kcoal_done = true;
+    };
+    rc = score_batch_impl(ctx, obs, trees, n, params, ref_denom, out_k, out_denom, khat.data(), use_kcoal ? &overlap : nullptr);
+    const double t2 = trace ? now() : 0.0;
+    if (rc == PK_OK && use_kcoal) {
+        if (!kcoal_done) overlap();
+        if (rc_kcoal) rc = pk_fail(rc_kcoal, err_kcoal);
     }
     if (rc == PK_OK) {
         double sum = 0.0;
