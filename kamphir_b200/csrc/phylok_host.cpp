@@ -125,7 +125,8 @@ namespace {
 
 // one node per token-created clade; all fields of a node share a cache line (the parser appends one node per '(' or ',')
 struct RawNode {
-    int32_t parent, first, last, next, nchild, name_off, name_len, pad;
+    int32_t parent, first, last, next, nchild, name_off, name_len;
+    int32_t ntip;                            // terminals below (the node itself if it is one); complete once the node is closed
     double bl;                               // NaN = absent (Biopython: None)
 };
 struct RawTree {
@@ -157,7 +158,7 @@ struct RawTree {
 // per-worker scratch of flatten(): capacities survive from tree to tree
 struct Scratch {
     RawTree raw;
-    std::vector<int32_t> pre, stack, ntip, kids, post, pidx;
+    std::vector<int32_t> kids, pidx, lvl;
     std::vector<double> depth, lens;
     std::vector<std::pair<int32_t, int32_t>> st;
     std::string err;
@@ -238,13 +239,41 @@ slow:
 
 // One tree from text[b, e) (no terminating ';').  Same token semantics as Biopython's Newick parser:
 // children in input order, '[...]' comments dropped, quoted labels, a ',' at top level creates a new root.
-int parse_one(const char *text, size_t b, size_t e, RawTree &t, std::string &err) {
+// The terminal counts are accumulated as clades are closed, and with `ladderize` the children of a clade are put in
+// ladder order (ascending terminal count, stable: Bio.Phylo's ladderize, kamphir.py:154,280) the moment its ')' is read --
+// the count of a clade does not depend on the order of anything, so sorting bottom-up while parsing gives the same
+// tree as the reference's recursive top-down sort.
+int parse_one(const char *text, size_t b, size_t e, RawTree &t, bool ladderize, std::vector<int32_t> &kids,
+              std::string &err) {
     t.clear();
     t.reserve((e - b) / 12 + 16);
     int32_t cur = t.add(-1);
     t.root = cur;
     long lp = 0, rp = 0;
     bool synthetic_root = false;
+    std::vector<RawNode> &nd = t.nd;
+    auto close = [&](int32_t v) {            // v will get no more children: its terminal count is final
+        if (nd[v].first < 0) nd[v].ntip = 1;
+        if (nd[v].parent >= 0) nd[nd[v].parent].ntip += nd[v].ntip;
+    };
+    auto ladder = [&](int32_t v) {
+        if (nd[v].nchild == 2) {             // binary node: swap only when strictly larger first (stable on ties)
+            const int32_t x = nd[v].first, y = nd[x].next;
+            if (nd[x].ntip > nd[y].ntip) {
+                nd[v].first = y;
+                nd[y].next = x;
+                nd[x].next = -1;
+                nd[v].last = x;
+            }
+        } else if (nd[v].nchild > 2) {
+            kids.clear();
+            for (int32_t c = nd[v].first; c >= 0; c = nd[c].next) kids.push_back(c);
+            std::stable_sort(kids.begin(), kids.end(), [&](int32_t a, int32_t c) { return nd[a].ntip < nd[c].ntip; });
+            nd[v].first = kids.front();
+            nd[v].last = kids.back();
+            for (size_t k = 0; k < kids.size(); ++k) nd[kids[k]].next = (k + 1 < kids.size()) ? kids[k + 1] : -1;
+        }
+    };
     size_t i = b;
     while (i < e) {
         char ch = text[i];
@@ -253,7 +282,7 @@ int parse_one(const char *text, size_t b, size_t e, RawTree &t, std::string &err
             cur = t.add(cur);
             ++lp; ++i;
         } else if (ch == ',') {
-            int32_t par = t.nd[cur].parent;
+            int32_t par = nd[cur].parent;
             if (par < 0) {                 // outer parentheses missing: new root above the current clade
                 int32_t nr = t.add(-1);
                 t.link(nr, cur);
@@ -261,12 +290,15 @@ int parse_one(const char *text, size_t b, size_t e, RawTree &t, std::string &err
                 par = nr;
                 synthetic_root = true;
             }
+            close(cur);
             cur = t.add(par);
             ++i;
         } else if (ch == ')') {
-            int32_t par = t.nd[cur].parent;
+            int32_t par = nd[cur].parent;
             if (par < 0) { err = "Newick: parenthesis mismatch"; return PK_ERR_PARSE; }
+            close(cur);
             cur = par;
+            if (ladderize) ladder(cur);
             ++rp; ++i;
         } else if (ch == ':') {
             size_t j = i + 1;
@@ -280,14 +312,14 @@ int parse_one(const char *text, size_t b, size_t e, RawTree &t, std::string &err
                 err = "Newick: bad branch length '" + std::string(text + j, k - j) + "'";
                 return PK_ERR_PARSE;
             }
-            t.nd[cur].bl = v;
+            nd[cur].bl = v;
             i = k;
         } else if (ch == '\'') {
             size_t j = i + 1;
             while (j < e && text[j] != '\'') ++j;
             if (j >= e) { err = "Newick: unterminated quoted label"; return PK_ERR_PARSE; }
-            t.nd[cur].name_off = (int32_t)(i + 1 - b);
-            t.nd[cur].name_len = (int32_t)(j - i - 1);
+            nd[cur].name_off = (int32_t)(i + 1 - b);
+            nd[cur].name_len = (int32_t)(j - i - 1);
             i = j + 1;
         } else if (ch == '[') {
             size_t j = i + 1;
@@ -302,16 +334,21 @@ int parse_one(const char *text, size_t b, size_t e, RawTree &t, std::string &err
         } else {
             size_t k = i;
             while (k < e && !is_token_end(text[k])) ++k;
-            t.nd[cur].name_off = (int32_t)(i - b);
-            t.nd[cur].name_len = (int32_t)(k - i);
+            nd[cur].name_off = (int32_t)(i - b);
+            nd[cur].name_len = (int32_t)(k - i);
             i = k;
         }
     }
     if (lp != rp) { err = "Newick: number of open/close parentheses do not match"; return PK_ERR_PARSE; }
-    if (cur != t.root && !(synthetic_root && t.nd[cur].parent == t.root)) {
+    if (cur != t.root && !(synthetic_root && nd[cur].parent == t.root)) {
         err = "Newick: parenthesis mismatch";
         return PK_ERR_PARSE;
     }
+    if (cur != t.root) {                   // synthetic root: its last child and the root itself were never closed by a ')'
+        close(cur);
+        if (ladderize) ladder(t.root);
+    }
+    if (nd[t.root].first < 0) nd[t.root].ntip = 1;       // a lone tip
     return PK_OK;
 }
 
@@ -373,182 +410,71 @@ int tip_state(const char *text, const RawTree &t, int32_t v, int nstates, int &s
     return PK_OK;
 }
 
-// RawTree -> pk_tree following kamphir's prep order.
+// RawTree (already in ladder order if asked for) -> pk_tree following kamphir's prep order, in ONE depth-first
+// traversal: on the way down the un-normalised depths and the pre-order sum of the branch lengths (the order Bio.Phylo's
+// total_branch_length adds them in -- the mean must come out bit-identical), on the way up the post-order numbering of
+// annotate_tree with the children's indices, classes and wavefront levels.
 int flatten(const char *text, Scratch &sc, int flags, int normalize, int nstates, pk_tree &out, std::string &err) {
     RawTree &r = sc.raw;
     std::vector<RawNode> &nd = r.nd;
     const int32_t total = (int32_t)r.size();
     const int32_t root = r.root;
-    const double NaN = std::numeric_limits<double>::quiet_NaN();
-
-    // pre-order (node, then children in order); its reverse serves the bottom-up passes
-    std::vector<int32_t> &pre = sc.pre, &stack = sc.stack;
-    auto preorder = [&]() {
-        pre.clear();
-        stack.clear();
-        stack.push_back(root);
-        while (!stack.empty()) {
-            int32_t v = stack.back();
-            stack.pop_back();
-            pre.push_back(v);
-            const size_t base = stack.size();
-            for (int32_t c = nd[v].first; c >= 0; c = nd[c].next) stack.push_back(c);
-            std::reverse(stack.begin() + base, stack.end());
-        }
-    };
-    preorder();
-
-    if (flags & PK_PREP_ZERO_ROOT) nd[root].bl = 0.0;                      // kamphir.py:153,279
-
-    if (flags & PK_PREP_LADDERIZE) {                                       // kamphir.py:154,280
-        std::vector<int32_t> &ntip = sc.ntip;
-        ntip.assign(total, 0);
-        for (size_t k = pre.size(); k-- > 0;) {
-            int32_t v = pre[k];
-            if (nd[v].first < 0) ntip[v] = 1;
-            if (nd[v].parent >= 0) ntip[nd[v].parent] += ntip[v];
-        }
-        bool changed = false;
-        std::vector<int32_t> &kids = sc.kids;
-        for (int32_t v = 0; v < total; ++v) {
-            if (nd[v].nchild < 2) continue;
-            if (nd[v].nchild == 2) {       // binary node: swap only when strictly larger first (stable on ties)
-                const int32_t x = nd[v].first, y = nd[x].next;
-                if (ntip[x] > ntip[y]) {
-                    nd[v].first = y;
-                    nd[y].next = x;
-                    nd[x].next = -1;
-                    nd[v].last = x;
-                    changed = true;
-                }
-                continue;
-            }
-            kids.clear();
-            for (int32_t c = nd[v].first; c >= 0; c = nd[c].next) kids.push_back(c);
-            std::stable_sort(kids.begin(), kids.end(), [&](int32_t a, int32_t b) { return ntip[a] < ntip[b]; });
-            nd[v].first = kids.front();
-            nd[v].last = kids.back();
-            for (size_t k = 0; k < kids.size(); ++k) nd[kids[k]].next = (k + 1 < kids.size()) ? kids[k + 1] : -1;
-            changed = true;
-        }
-        if (changed) preorder();
-    }
-
-    // un-normalised depths / node heights (kamphir.py:118-119,147-149,255-258); None counts as 0
-    {
-        std::vector<double> &depth = sc.depth;
-        depth.assign(total, 0.0);
-        double hmax = 0.0;
-        bool firstv = true;
-        for (int32_t v : pre) {
-            double b = std::isnan(nd[v].bl) ? 0.0 : nd[v].bl;
-            depth[v] = (nd[v].parent >= 0 ? depth[nd[v].parent] : 0.0) + b;
-            if (firstv || depth[v] > hmax) hmax = depth[v];
-            firstv = false;
-        }
-        out.height = hmax;
-        out.heights.clear();
-        out.heights.reserve((size_t)total / 2 + 1);
-        for (int32_t v : pre)
-            if (nd[v].first >= 0) out.heights.push_back(hmax - depth[v]);
-        out.heights_sorted = false;    // sorted on first use: pk_kcoal_batch spreads that over the worker pool
-    }
-
-    // normalize_tree (phyloK2.py:101-130): every non-root branch divided by the mean / median
-    out.scale = 1.0;
-    if (normalize == PK_NORM_MEAN || normalize == PK_NORM_MEDIAN) {
-        const int32_t nbranches = total - 1;                               // :109
-        if (nbranches < 1) { err = "normalize_tree: tree has no branches"; return PK_ERR_INVALID; }
-        double scale;
-        if (normalize == PK_NORM_MEAN) {
-            double sum = 0.0;                                              // total_branch_length(): truthy lengths, pre-order
-            for (int32_t v : pre) {
-                double b = nd[v].bl;
-                if (!std::isnan(b) && b != 0.0) sum = sum + b;
-            }
-            double rootbl = std::isnan(nd[root].bl) ? 0.0 : nd[root].bl;   // reference: TypeError on None (phyloK2.py:113)
-            scale = (sum - rootbl) / nbranches;
-        } else {
-            std::vector<double> &lens = sc.lens;
-            lens.clear();
-            lens.reserve(nbranches);
-            for (int32_t v : pre) {
-                if (v == root) continue;
-                if (std::isnan(nd[v].bl)) { err = "normalize_tree: branch without a length"; return PK_ERR_INVALID; }
-                lens.push_back(nd[v].bl);
-            }
-            std::sort(lens.begin(), lens.end());
-            int32_t half = nbranches / 2;                                  // py2 integer division, :123-127
-            scale = (nbranches % 2 == 0) ? (lens[half - 1] + lens[half]) / 2. : lens[half];
-        }
-        if (!(scale != 0.0) || !std::isfinite(scale)) {
-            err = "normalize_tree: zero or non-finite scale (reference: ZeroDivisionError)";
-            return PK_ERR_INVALID;
-        }
-        for (int32_t v = 0; v < total; ++v)
-            if (v != root && !std::isnan(nd[v].bl)) nd[v].bl /= scale;
-        out.scale = scale;
-    } else if (normalize != PK_NORM_NONE) {
+    if (normalize != PK_NORM_MEAN && normalize != PK_NORM_MEDIAN && normalize != PK_NORM_NONE) {
         err = "unknown normalize mode";
         return PK_ERR_INVALID;
     }
+    if (flags & PK_PREP_ZERO_ROOT) nd[root].bl = 0.0;                      // kamphir.py:153,279
 
-    // annotate_tree (phyloK2.py:132-146): internal nodes in post-order
-    std::vector<int32_t> &post = sc.post;
-    post.clear();
-    post.reserve(total);
-    {
-        // iterative post-order: children (in order) before the parent
-        std::vector<std::pair<int32_t, int32_t>> &st = sc.st;   // (node, next child to visit)
-        st.clear();
-        st.emplace_back(root, nd[root].first);
-        while (!st.empty()) {
-            auto &top = st.back();
-            if (top.second >= 0) {
-                int32_t c = top.second;
-                top.second = nd[c].next;
-                st.emplace_back(c, nd[c].first);
-            } else {
-                post.push_back(top.first);
-                st.pop_back();
-            }
-        }
-    }
-    std::vector<int32_t> &pidx = sc.pidx;
-    pidx.assign(total, -1);
-    int32_t n = 0, ntips = 0;
-    for (int32_t v : post) {
-        if (nd[v].first >= 0) pidx[v] = n++; else ++ntips;
-    }
-    if (n == 0) { err = "tree has no internal node (reference: IndexError at phyloK2.py:169)"; return PK_ERR_INVALID; }
-    out.n = n;
-    out.ntips = ntips;
+    const int32_t n_internal = total - nd[root].ntip;
+    if (n_internal < 1) { err = "tree has no internal node (reference: IndexError at phyloK2.py:169)"; return PK_ERR_INVALID; }
+    out.n = n_internal;
+    out.ntips = nd[root].ntip;
     out.nstates = nstates;
     out.ncls = nstates > 0 ? 1 + 2 * nstates + nstates * nstates : 3;
     if (out.ncls > PK_MAX_CLASSES) { err = "too many tip states (max 7)"; return PK_ERR_INVALID; }
-    out.prod.assign(n, 0);
-    out.cls.assign(n, 0);
-    out.cidx.assign(2 * (size_t)n, -1);
-    out.bl.assign(2 * (size_t)n, NaN);
-    for (int32_t v : post) {
-        if (nd[v].first < 0) continue;
-        int32_t i = pidx[v];
+    const double NaN = std::numeric_limits<double>::quiet_NaN();
+    out.prod.assign(n_internal, 0);
+    out.cls.assign(n_internal, 0);
+    out.cidx.assign(2 * (size_t)n_internal, -1);
+    out.bl.assign(2 * (size_t)n_internal, NaN);
+    out.level.assign(n_internal, 0);
+    out.heights.clear();
+    out.heights.reserve((size_t)n_internal);
+
+    std::vector<double> &depth = sc.depth;
+    std::vector<int32_t> &pidx = sc.pidx;
+    depth.resize(total);
+    pidx.assign(total, -1);
+    std::vector<double> &lens = sc.lens;
+    lens.clear();
+    double sum = 0.0, hmax = 0.0;
+    bool firstv = true;
+    int32_t next_idx = 0;
+    const bool median = normalize == PK_NORM_MEDIAN;
+
+    auto enter = [&](int32_t v) {                                          // pre-order visit
+        const double bl = nd[v].bl;
+        const double b = std::isnan(bl) ? 0.0 : bl;                        // depths: None counts as 0 (kamphir.py:118-119)
+        depth[v] = (nd[v].parent >= 0 ? depth[nd[v].parent] : 0.0) + b;
+        if (firstv || depth[v] > hmax) hmax = depth[v];
+        firstv = false;
+        if (!std::isnan(bl) && bl != 0.0) sum = sum + bl;                  // total_branch_length(): truthy lengths
+        if (median && v != root) lens.push_back(bl);
+        if (nd[v].first >= 0) out.heights.push_back(depth[v]);             // turned into heights below
+    };
+    auto leave = [&](int32_t v) -> int {                                   // post-order visit of an internal node
+        const int32_t i = next_idx++;
+        pidx[v] = i;
         if (nd[v].nchild != 2) {
             err = "internal node " + std::to_string(i) + " has " + std::to_string(nd[v].nchild) +
                   " children; the kernel is defined for strictly binary trees (reference: IndexError at phyloK2.py:185-189)";
             return PK_ERR_INVALID;
         }
-        int32_t kid[2] = {nd[v].first, nd[nd[v].first].next};
-        int nterm = 0, st[2] = {-1, -1};
+        const int32_t kid[2] = {nd[v].first, nd[nd[v].first].next};
+        int nterm = 0, st[2] = {-1, -1}, lv = 0;
         for (int s = 0; s < 2; ++s) {
-            int32_t c = kid[s];
-            double b = nd[c].bl;
-            if (!std::isfinite(b)) {
-                err = std::isnan(b) ? "branch without a length (reference: TypeError at phyloK2.py:146)"
-                                    : "non-finite branch length";
-                return PK_ERR_INVALID;
-            }
-            out.bl[2 * (size_t)i + s] = b;
+            const int32_t c = kid[s];
+            out.bl[2 * (size_t)i + s] = nd[c].bl;                          // rescaled and checked after the traversal
             if (nd[c].first < 0) {
                 ++nterm;
                 if (nstates > 0) {
@@ -557,42 +483,101 @@ int flatten(const char *text, Scratch &sc, int flags, int normalize, int nstates
                 }
             } else {
                 out.cidx[2 * (size_t)i + s] = pidx[c];
+                lv = std::max(lv, out.level[pidx[c]] + 1);
             }
         }
-        out.prod[i] = (uint8_t)(nterm + 1);                                 // :141-142
+        out.level[i] = lv;
+        out.prod[i] = (uint8_t)(nterm + 1);                                 // phyloK2.py:141-142
         if (nstates == 0) {
             out.cls[i] = (uint8_t)nterm;
         } else if (nterm == 0) {
             out.cls[i] = 0;
         } else if (nterm == 1) {
-            int slot = st[0] >= 0 ? 0 : 1;
+            const int slot = st[0] >= 0 ? 0 : 1;
             out.cls[i] = (uint8_t)(1 + slot * nstates + st[slot]);
         } else {
             out.cls[i] = (uint8_t)(1 + 2 * nstates + st[0] * nstates + st[1]);
         }
+        return PK_OK;
+    };
+    {
+        std::vector<std::pair<int32_t, int32_t>> &st = sc.st;              // (node, next child to visit)
+        st.clear();
+        enter(root);
+        st.emplace_back(root, nd[root].first);
+        while (!st.empty()) {
+            auto &top = st.back();
+            if (top.second >= 0) {
+                const int32_t c = top.second;
+                top.second = nd[c].next;
+                enter(c);
+                if (nd[c].first >= 0) st.emplace_back(c, nd[c].first);
+            } else {
+                const int rc = leave(top.first);
+                if (rc != PK_OK) return rc;
+                st.pop_back();
+            }
+        }
     }
-    return pk_tree_finish(out);
+    // node heights for kcoal (kamphir.py:255-258), un-normalised; sorted on first use (pk_sorted_heights)
+    out.height = hmax;
+    for (double &h : out.heights) h = hmax - h;
+    out.heights_sorted = false;
+
+    // normalize_tree (phyloK2.py:101-130): every non-root branch divided by the mean / median
+    out.scale = 1.0;
+    if (normalize == PK_NORM_MEAN || median) {
+        const int32_t nbranches = total - 1;                               // :109
+        if (nbranches < 1) { err = "normalize_tree: tree has no branches"; return PK_ERR_INVALID; }
+        double scale;
+        if (!median) {
+            const double rootbl = std::isnan(nd[root].bl) ? 0.0 : nd[root].bl;   // reference: TypeError on None (phyloK2.py:113)
+            scale = (sum - rootbl) / nbranches;
+        } else {
+            for (double b : lens)
+                if (std::isnan(b)) { err = "normalize_tree: branch without a length"; return PK_ERR_INVALID; }
+            std::sort(lens.begin(), lens.end());
+            const int32_t half = nbranches / 2;                            // py2 integer division, :123-127
+            scale = (nbranches % 2 == 0) ? (lens[half - 1] + lens[half]) / 2. : lens[half];
+        }
+        if (!(scale != 0.0) || !std::isfinite(scale)) {
+            err = "normalize_tree: zero or non-finite scale (reference: ZeroDivisionError)";
+            return PK_ERR_INVALID;
+        }
+        for (double &b : out.bl) b /= scale;                               // every entry is a non-root branch; NaN stays NaN
+        out.scale = scale;
+    }
+    for (double b : out.bl)
+        if (!std::isfinite(b)) {
+            err = std::isnan(b) ? "branch without a length (reference: TypeError at phyloK2.py:146)" : "non-finite branch length";
+            return PK_ERR_INVALID;
+        }
+    return pk_tree_finish(out, /*levels_known=*/true);
 }
 
 }  // namespace
 
 // levels, kernel order, per-class level table, child-class histograms
-int pk_tree_finish(pk_tree &t) {
+int pk_tree_finish(pk_tree &t, bool levels_known) {
     const int32_t n = t.n, ncls = t.ncls;
-    t.level.assign(n, 0);
     int32_t nlev = 1;
-    for (int32_t i = 0; i < n; ++i) {
-        int32_t lv = 0;
-        for (int s = 0; s < 2; ++s) {
-            int32_t c = t.cidx[2 * (size_t)i + s];
-            if (c >= 0) {
-                if (c >= i) return pk_fail(PK_ERR_INVALID, "child index is not below its parent in post-order");
-                lv = std::max(lv, t.level[c] + 1);
+    if (levels_known) {                    // the flattener computed them on its way up
+        for (int32_t i = 0; i < n; ++i) nlev = std::max(nlev, t.level[i] + 1);
+    } else {
+        t.level.assign(n, 0);
+        for (int32_t i = 0; i < n; ++i) {
+            int32_t lv = 0;
+            for (int s = 0; s < 2; ++s) {
+                int32_t c = t.cidx[2 * (size_t)i + s];
+                if (c >= 0) {
+                    if (c >= i) return pk_fail(PK_ERR_INVALID, "child index is not below its parent in post-order");
+                    lv = std::max(lv, t.level[c] + 1);
+                }
             }
+            t.level[i] = lv;
+            nlev = std::max(nlev, lv + 1);
+            if (t.cls[i] >= ncls) return pk_fail(PK_ERR_INVALID, "class id out of range");
         }
-        t.level[i] = lv;
-        nlev = std::max(nlev, lv + 1);
-        if (t.cls[i] >= ncls) return pk_fail(PK_ERR_INVALID, "class id out of range");
     }
     t.nlev = nlev;
     // counting sort by (class, level); stable in post-order index
@@ -804,7 +789,7 @@ extern "C" int pk_tree_from_newick(const char *text, size_t len, int prep_flags,
     static thread_local Scratch sc;
     RawTree &raw = sc.raw;
     std::string err;
-    int rc = parse_one(text, ranges[0].first, ranges[0].second, raw, err);
+    int rc = parse_one(text, ranges[0].first, ranges[0].second, raw, (prep_flags & PK_PREP_LADDERIZE) != 0, sc.kids, err);
     if (rc != PK_OK) return pk_fail(rc, err);
     pk_tree *t = new (std::nothrow) pk_tree();
     if (!t) return pk_fail(PK_ERR_NOMEM, "out of memory");
@@ -873,7 +858,7 @@ static int flatten_many(const std::vector<const char *> &bases, const std::vecto
             size_t k = next.fetch_add(1);
             if (k >= nt || status.load() != PK_OK) break;
             const char *text = bases[k];
-            int rc = parse_one(text, ranges[k].first, ranges[k].second, raw, err);
+            int rc = parse_one(text, ranges[k].first, ranges[k].second, raw, (prep_flags & PK_PREP_LADDERIZE) != 0, sc.kids, err);
             if (rc == PK_OK) {
                 arr[k] = new (std::nothrow) pk_tree();
                 if (!arr[k]) { rc = PK_ERR_NOMEM; err = "out of memory"; }

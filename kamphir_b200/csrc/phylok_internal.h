@@ -76,4 +76,4 @@ void pk_set_error(const std::string &msg);
 int pk_fail(int code, const std::string &msg);
 
 // finishes a tree whose post-order arrays (prod/cls/cidx/bl, n, ncls) are filled: levels, kernel order, histograms
-int pk_tree_finish(pk_tree &t);
+int pk_tree_finish(pk_tree &t, bool levels_known = false);
