@@ -119,6 +119,13 @@ int pk_ctx_configure(pk_ctx *ctx, int32_t threads, int32_t ctas_per_sm, int32_t 
 int pk_ctx_last_stats(pk_ctx *ctx, double *ms, int64_t *launches, int32_t *path, int32_t launch_cfg[3]);
 
 int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_t n, int32_t precision, pk_forest **out);
+/* Multi-GPU replication of a forest without packing it W times: every rank lays the whole forest out (same offsets,
+ * same meta records, same host-side statistics) but packs and uploads only the trees [part_lo, part_hi); the ranks then
+ * exchange their byte ranges device-to-device over NVLink (pk_forest_device_range gives the pointer and size of a tree
+ * range; kamphir_b200/gram.py broadcasts them with NCCL).  The forest must not be used before the exchange is done. */
+int pk_forest_upload_part(pk_ctx *ctx, const pk_tree *const *trees, int32_t n, int32_t precision, int32_t part_lo,
+                          int32_t part_hi, pk_forest **out);
+int pk_forest_device_range(const pk_forest *f, int32_t tree_lo, int32_t tree_hi, void **d_ptr, int64_t *bytes);
 void pk_forest_free(pk_forest *f);
 int pk_forest_bytes(const pk_forest *f, int64_t *bytes);
 /* exact work of a pair list / of one Gram part: counts = {DPs, node pairs, matched cells M, child reads R} */
@@ -164,6 +171,9 @@ int pk_gram_part_pairs(int32_t n, int32_t tile, int32_t part, int32_t nparts, in
 int pk_gram_part_tiles(int32_t n, int32_t tile, int32_t part, int32_t nparts, int32_t *tiles, int64_t *ntiles);
 
 /* cross-process sharing of a device buffer (one result matrix on rank 0, written by all ranks over NVLink) */
+/* page-locked host buffers for results fetched every step (GramRunner.fetch) */
+int pk_host_alloc(pk_ctx *ctx, size_t bytes, void **h_ptr);
+int pk_host_free(pk_ctx *ctx, void *h_ptr);
 int pk_device_alloc(pk_ctx *ctx, size_t bytes, void **d_ptr);
 int pk_device_free(pk_ctx *ctx, void *d_ptr);
 int pk_ipc_export(pk_ctx *ctx, void *d_ptr, unsigned char handle[64]);

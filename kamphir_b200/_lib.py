@@ -52,6 +52,8 @@ SIGNATURES = {
     "pk_ctx_configure": (ctypes.c_int, [_P, _I32, _I32, _I32]),
     "pk_ctx_last_stats": (ctypes.c_int, [_P, ctypes.POINTER(_D), ctypes.POINTER(_I64), ctypes.POINTER(_I32), _P]),
     "pk_forest_upload": (ctypes.c_int, [_P, _P, _I32, _I32, _PP]),
+    "pk_forest_upload_part": (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _I32, _PP]),
+    "pk_forest_device_range": (ctypes.c_int, [_P, _I32, _I32, _PP, ctypes.POINTER(_I64)]),
     "pk_forest_free": (None, [_P]),
     "pk_forest_bytes": (ctypes.c_int, [_P, ctypes.POINTER(_I64)]),
     "pk_forest_pair_stats": (ctypes.c_int, [_P, _P, _P, _I64, _P]),
@@ -66,6 +68,8 @@ SIGNATURES = {
     "pk_forest_gram_part": (ctypes.c_int, [_P, _P, ctypes.POINTER(pk_params), ctypes.c_int, _I32, _I32, _I32, _P, _I64, _P]),
     "pk_gram_part_pairs": (ctypes.c_int, [_I32, _I32, _I32, _I32, ctypes.POINTER(_I64)]),
     "pk_gram_part_tiles": (ctypes.c_int, [_I32, _I32, _I32, _I32, _P, ctypes.POINTER(_I64)]),
+    "pk_host_alloc": (ctypes.c_int, [_P, _SZ, _PP]),
+    "pk_host_free": (ctypes.c_int, [_P, _P]),
     "pk_device_alloc": (ctypes.c_int, [_P, _SZ, _PP]),
     "pk_device_free": (ctypes.c_int, [_P, _P]),
     "pk_ipc_export": (ctypes.c_int, [_P, _P, _P]),

@@ -692,6 +692,7 @@ struct pk_forest {
     std::vector<int32_t> cnt;       // [n][ncls]
     std::vector<int64_t> hist;      // [n][ncls*2*(ncls+1)]
     std::vector<int32_t> nint;      // [n]
+    std::vector<size_t> offs;       // [n + 1] byte offset of every tree's block in d_blocks
 };
 
 static const int kCounterRing = 64;
@@ -879,9 +880,13 @@ static void pool_release(pk_ctx *ctx, void *ptr, size_t bytes) {
     }
 }
 
-extern "C" int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_t n, int32_t precision, pk_forest **out) {
+// [part_lo, part_hi): the trees this call packs and copies to the device (all of them for a plain upload); the layout,
+// the per-part meta records and the host-side statistics always cover the whole set
+static int forest_upload_impl(pk_ctx *ctx, const pk_tree *const *trees, int32_t n, int32_t precision, int32_t part_lo,
+                              int32_t part_hi, pk_forest **out) {
     if (!ctx || !trees || !out) return pk_fail(PK_ERR_INVALID, "null argument");
     if (n < 1) return pk_fail(PK_ERR_INVALID, "empty tree set");
+    if (part_lo < 0 || part_hi > n || part_lo > part_hi) return pk_fail(PK_ERR_INVALID, "tree range out of bounds");
     if (precision != 64 && precision != 32) return pk_fail(PK_ERR_INVALID, "precision must be 64 or 32");
     *out = nullptr;
     int rc = ensure_device(ctx);
@@ -923,13 +928,17 @@ extern "C" int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_
     auto pack_range = [&](int32_t lo, int32_t hi) {
         for (int32_t i = lo; i < hi; ++i) {
             const pk_tree &t = *trees[i];
-            const size_t off = offs[i], rb = pk_rowpart_bytes(t, precision), cb = pk_colpart_bytes(t, precision);
+            const size_t off = offs[i], rb = pk_rowpart_bytes(t, precision);
             pk_rowpart_pack(t, precision, h + off);
             pk_colpart_pack(t, precision, h + off + rb);
-            hmeta[2 * i] = make_int4((int)(off / 16), (int)rb, t.n, t.nlev);            // row part
-            hmeta[2 * i + 1] = make_int4((int)((off + rb) / 16), (int)cb, t.n, t.nlev);   // column part
         }
     };
+    for (int32_t i = 0; i < n; ++i) {
+        const pk_tree &t = *trees[i];
+        const size_t off = offs[i], rb = pk_rowpart_bytes(t, precision), cb = pk_colpart_bytes(t, precision);
+        hmeta[2 * i] = make_int4((int)(off / 16), (int)rb, t.n, t.nlev);            // row part
+        hmeta[2 * i + 1] = make_int4((int)((off + rb) / 16), (int)cb, t.n, t.nlev);   // column part
+    }
     // Device buffer first, then pack and copy in phases: while the cores pack phase p + 1 into the pinned buffer, the
     // copy engine moves phase p (a 31 MB forest of 256 x 2000-tip trees: ~1.3 ms of copy hidden behind the packing).
     void *dptr = nullptr;
@@ -937,10 +946,13 @@ extern "C" int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_
     f->d_blocks = static_cast<unsigned char *>(dptr);
     if (e == cudaSuccess) {
         f->d_meta = reinterpret_cast<int4 *>(f->d_blocks + total);
-        const int nthr = (int)std::min<size_t>(std::min(pk_host_threads(), 32), std::max<size_t>(1, total / ((size_t)128 << 10)));
-        const int nphase = (int)std::min<size_t>(8, std::max<size_t>(1, total / ((size_t)4 << 20)));
+        const size_t part_bytes = offs[part_hi] - offs[part_lo];
+        const int32_t pn = part_hi - part_lo;
+        const int nthr = (int)std::min<size_t>(std::min(pk_host_threads(), 32), std::max<size_t>(1, part_bytes / ((size_t)128 << 10)));
+        const int nphase = (int)std::min<size_t>(8, std::max<size_t>(1, part_bytes / ((size_t)4 << 20)));
         for (int ph = 0; ph < nphase && e == cudaSuccess; ++ph) {
-            const int32_t p_lo = (int32_t)((int64_t)n * ph / nphase), p_hi = (int32_t)((int64_t)n * (ph + 1) / nphase);
+            const int32_t p_lo = part_lo + (int32_t)((int64_t)pn * ph / nphase),
+                          p_hi = part_lo + (int32_t)((int64_t)pn * (ph + 1) / nphase);
             std::atomic<int32_t> next{p_lo};
             const int32_t chunk = std::max<int32_t>(1, (p_hi - p_lo) / (nthr * 4));
             pk_parallel(nthr, [&](int) {
@@ -983,7 +995,25 @@ extern "C" int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_
         cudaGetLastError();
         return pk_fail(PK_ERR_CUDA, std::string("pk_forest_upload: ") + cudaGetErrorString(e));
     }
+    f->offs = offs;
     *out = f;
+    return PK_OK;
+}
+
+extern "C" int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_t n, int32_t precision, pk_forest **out) {
+    return forest_upload_impl(ctx, trees, n, precision, 0, n, out);
+}
+
+extern "C" int pk_forest_upload_part(pk_ctx *ctx, const pk_tree *const *trees, int32_t n, int32_t precision,
+                                     int32_t part_lo, int32_t part_hi, pk_forest **out) {
+    return forest_upload_impl(ctx, trees, n, precision, part_lo, part_hi, out);
+}
+
+extern "C" int pk_forest_device_range(const pk_forest *f, int32_t tree_lo, int32_t tree_hi, void **d_ptr, int64_t *bytes) {
+    if (!f || !d_ptr || !bytes) return pk_fail(PK_ERR_INVALID, "null argument");
+    if (tree_lo < 0 || tree_hi > f->n || tree_lo > tree_hi) return pk_fail(PK_ERR_INVALID, "tree range out of bounds");
+    *d_ptr = f->d_blocks + f->offs[tree_lo];
+    *bytes = (int64_t)(f->offs[tree_hi] - f->offs[tree_lo]);
     return PK_OK;
 }
 
@@ -1546,6 +1576,22 @@ extern "C" int pk_device_free(pk_ctx *ctx, void *d_ptr) {
     if (rc) return rc;
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
     PK_CUDA(cudaFree(d_ptr));
+    return PK_OK;
+}
+/* page-locked host memory for results that are fetched every step (a 134 MB matrix lands in pinned memory at PCIe speed;
+ * a fresh pageable array costs first-touch page faults and a staged copy) */
+extern "C" int pk_host_alloc(pk_ctx *ctx, size_t bytes, void **h_ptr) {
+    if (!ctx || !h_ptr) return pk_fail(PK_ERR_INVALID, "null argument");
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    PK_CUDA(cudaMallocHost(h_ptr, bytes));
+    return PK_OK;
+}
+extern "C" int pk_host_free(pk_ctx *ctx, void *h_ptr) {
+    if (!ctx) return pk_fail(PK_ERR_INVALID, "null argument");
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    PK_CUDA(cudaFreeHost(h_ptr));
     return PK_OK;
 }
 extern "C" int pk_ipc_export(pk_ctx *ctx, void *d_ptr, unsigned char handle[64]) {

@@ -43,6 +43,7 @@ class GramRunner(object):
         self.d_out = ctypes.c_void_p()        # where this rank's kernel writes (local or rank 0's mapped buffer)
         self.d_local = ctypes.c_void_p()      # buffer this rank owns (rank 0 always; all ranks for allreduce)
         self.d_diag = ctypes.c_void_p()
+        self.h_out = ctypes.c_void_p()        # page-locked host copy of the matrix (fetch)
         self._torch_view = None
         n = self.n
         check(self.L.pk_device_alloc(self.ctx._h, 8 * n, ctypes.byref(self.d_diag)))
@@ -70,11 +71,30 @@ class GramRunner(object):
             check(self.L.pk_ipc_open(self.ctx._h, raw, ctypes.byref(self.d_out)))
 
     def upload(self):
-        """Host trees -> packed device forest (the H2D leg of the end-to-end path). Returns bytes copied."""
+        """Host trees -> packed device forest on every rank (the H2D leg of the end-to-end path).  Returns the bytes
+        this rank copied from the host.
+
+        With W ranks each one packs and uploads 1/W of the trees and the ranks broadcast their byte ranges to each other
+        device-to-device (NCCL over NVLink): the host packs the forest once per box instead of once per GPU."""
         if self.forest is not None:
             self.forest.close()
-        self.forest = Forest(self.ctx, self.flats, self.precision)
-        return self.forest.nbytes()
+        if self.world == 1:
+            self.forest = Forest(self.ctx, self.flats, self.precision)
+            return self.forest.nbytes()
+        import torch.distributed as dist
+        cuts = [self.n * r // self.world for r in range(self.world + 1)]
+        self.forest = Forest(self.ctx, self.flats, self.precision, part=(cuts[self.rank], cuts[self.rank + 1]))
+        self.ctx.sync()
+        mine = 0
+        for r in range(self.world):
+            ptr, nbytes = self.forest.device_range(cuts[r], cuts[r + 1])
+            if r == self.rank:
+                mine = nbytes
+            if nbytes:
+                dist.broadcast(_as_tensor(ptr, nbytes, "|u1"), src=r, group=self.group)
+        import torch
+        torch.cuda.current_stream().synchronize()
+        return mine + 32 * self.n           # + the meta records every rank uploads
 
     # -- one step ---------------------------------------------------------------------------------------
     def launch(self):
@@ -103,11 +123,16 @@ class GramRunner(object):
         if self.d_local.value:
             check(self.L.pk_memset_d(self.ctx._h, self.d_local, 0, 8 * self.n * self.n))
 
-    def fetch(self):
-        """Device -> host copy of the full matrix (rank 0 for p2p; any rank otherwise)."""
-        out = np.empty((self.n, self.n), np.float64)
-        check(self.L.pk_memcpy_d2h(self.ctx._h, out.ctypes.data, self.d_local, 8 * self.n * self.n))
-        return out
+    def fetch(self, copy=False):
+        """Device -> host copy of the full matrix (rank 0 for p2p; any rank otherwise) into a page-locked buffer that
+        this runner owns and reuses: the returned array is a view of it (valid until the next fetch / close) unless
+        copy=True."""
+        nbytes = 8 * self.n * self.n
+        if not self.h_out.value:
+            check(self.L.pk_host_alloc(self.ctx._h, nbytes, ctypes.byref(self.h_out)))
+        check(self.L.pk_memcpy_d2h(self.ctx._h, self.h_out, self.d_local, nbytes))
+        view = np.ctypeslib.as_array(ctypes.cast(self.h_out, ctypes.POINTER(ctypes.c_double)), shape=(self.n, self.n))
+        return view.copy() if copy else view
 
     def my_stats(self):
         st = self.forest.gram_stats(self.tile, self.rank, self.world)
@@ -140,6 +165,9 @@ class GramRunner(object):
         if self.gather == "p2p" and self.rank != 0 and self.d_out.value:
             check(self.L.pk_ipc_close(self.ctx._h, self.d_out))
             self.d_out = ctypes.c_void_p()
+        if self.h_out.value:
+            check(self.L.pk_host_free(self.ctx._h, self.h_out))
+            self.h_out = ctypes.c_void_p()
         for buf in (self.d_local, self.d_diag):
             if buf.value:
                 check(self.L.pk_device_free(self.ctx._h, buf))
@@ -165,13 +193,13 @@ def part_pairs(n, tile, part, nparts):
     return cnt.value
 
 
-def _as_tensor(ptr, numel):
-    """Zero-copy torch view (float64) of a device buffer owned by libphylok (for the NCCL all-reduce only)."""
+def _as_tensor(ptr, numel, typestr="<f8"):
+    """Zero-copy torch view of a device buffer owned by libphylok (for the NCCL collectives only)."""
     import torch
 
     class _Holder(object):
         pass
 
     h = _Holder()
-    h.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+    h.__cuda_array_interface__ = {"shape": (numel,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
     return torch.as_tensor(h, device=torch.device("cuda", torch.cuda.current_device()))

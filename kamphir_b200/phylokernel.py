@@ -199,15 +199,27 @@ class Context(object):
 class Forest(object):
     """Device-resident packed SoA of a set of FlatTrees (``pk_forest*``)."""
 
-    def __init__(self, ctx, trees, precision=64):
+    def __init__(self, ctx, trees, precision=64, part=None):
+        """part=(lo, hi): pack and upload only those trees (the rest of the device forest is filled by the other ranks,
+        see GramRunner.upload); the layout and the statistics always cover the whole set."""
         self.ctx = ctx
         self.trees = list(trees)
         self.n = len(self.trees)
         self.precision = int(precision)
         arr = (ctypes.c_void_p * self.n)(*[t._h for t in self.trees])
         out = ctypes.c_void_p()
-        check(_lib.lib().pk_forest_upload(ctx._h, arr, self.n, self.precision, ctypes.byref(out)))
+        if part is None:
+            check(_lib.lib().pk_forest_upload(ctx._h, arr, self.n, self.precision, ctypes.byref(out)))
+        else:
+            check(_lib.lib().pk_forest_upload_part(ctx._h, arr, self.n, self.precision, int(part[0]), int(part[1]),
+                                                   ctypes.byref(out)))
         self._h = out
+
+    def device_range(self, lo, hi):
+        """(device pointer, bytes) of the packed blocks of trees [lo, hi)."""
+        ptr, nbytes = ctypes.c_void_p(), ctypes.c_int64()
+        check(_lib.lib().pk_forest_device_range(self._h, int(lo), int(hi), ctypes.byref(ptr), ctypes.byref(nbytes)))
+        return ptr.value or 0, nbytes.value
 
     def nbytes(self):
         b = ctypes.c_int64()

@@ -293,6 +293,46 @@ def test_gram_parts_tile_the_matrix():
     check(L.pk_device_free(ctx._h, d_diag))
 
 
+def test_forest_uploaded_in_parts_equals_plain_upload():
+    """The multi-GPU replication path on one GPU: two forests each pack half of the trees, the missing halves are copied
+    across (what the NCCL broadcasts do between ranks), and both then give the Gram matrix of a plain upload."""
+    import ctypes
+    from kamphir_b200 import Forest, _lib
+    from kamphir_b200._lib import check, pk_params
+    nwk = synth.tree_set(21, 70, 8800, "mixed")
+    flats = [FlatTree.from_newick(s) for s in nwk]
+    n, cut = len(flats), 9
+    ctx = get_context()
+    L = _lib.lib()
+    plain = Forest(ctx, flats, 64)
+    fa = Forest(ctx, flats, 64, part=(0, cut))
+    fb = Forest(ctx, flats, 64, part=(cut, n))
+    assert fa.nbytes() == fb.nbytes() == plain.nbytes()
+    for dst, src, lo, hi in ((fa, fb, cut, n), (fb, fa, 0, cut)):
+        sp, sb = src.device_range(lo, hi)
+        dp, db = dst.device_range(lo, hi)
+        assert sb == db > 0
+        host = np.empty(sb, np.uint8)
+        check(L.pk_memcpy_d2h(ctx._h, host.ctypes.data, ctypes.c_void_p(sp), sb))
+        check(L.pk_memcpy_h2d(ctx._h, ctypes.c_void_p(dp), host.ctypes.data, sb))
+    p = pk_params(0.2, 2.0, 1.0, 64, 0)
+    outs = []
+    for f in (plain, fa, fb):
+        d_out, d_diag = ctypes.c_void_p(), ctypes.c_void_p()
+        check(L.pk_device_alloc(ctx._h, 8 * n * n, ctypes.byref(d_out)))
+        check(L.pk_device_alloc(ctx._h, 8 * n, ctypes.byref(d_diag)))
+        check(L.pk_forest_gram_part(ctx._h, f._h, ctypes.byref(p), 1, 4, 0, 1, d_out, n, d_diag))
+        got = np.empty((n, n))
+        check(L.pk_memcpy_d2h(ctx._h, got.ctypes.data, d_out, 8 * n * n))
+        outs.append(got)
+        check(L.pk_device_free(ctx._h, d_out))
+        check(L.pk_device_free(ctx._h, d_diag))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    assert f.gram_stats(4) == plain.gram_stats(4)
+    for f in (plain, fa, fb):
+        f.close()
+
+
 def test_labelled_tip_states_against_extension_oracle():
     """configs[2] extension (no reference implementation, parity unpinned): class = production + tip-child states."""
     S = 2
