@@ -68,7 +68,7 @@ struct DpArgs {
     int tree_region;                // shared-memory bytes reserved for the staged ROW part
     int col_region;                 // ... and for the staged COLUMN part
     int rowinfo_bytes;              // row offsets
-    double bscale;                  // fp64: sqrt(64 / (ln2 tau)), applied to the staged branch lengths
+    double bscale;                  // sqrt(64 / (ln2 tau)) (fp64) or sqrt(1 / (ln2 tau)) (fp32), applied to the staged branch lengths
     int clamp_hi;                   // fp64 Gaussian: clamp of the exponent's high word
     unsigned long long exp_tab[64]; // fp64 Gaussian: bits of lambda * 2^(j/64) with the high word biased by -(j << 14)
 };
@@ -155,10 +155,15 @@ __device__ __forceinline__ void pk_gauss(const double (&E)[U], double (&out)[U],
         out[u] = q[u] * __hiloint2double(hi + (k << 14), (int)lo);
     }
 }
+// fp32: the lengths are pre-scaled by sqrt(log2(e) / tau), so lambda * exp(-d^2/tau) = lambda * 2^(-E): one MUFU.EX2
 template <int U>
 __device__ __forceinline__ void pk_gauss(const float (&E)[U], float (&out)[U], const GaussK<float> &gk) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) out[u] = gk.lambda * __expf(E[u] * gk.neg_inv_tau);
+    for (int u = 0; u < U; ++u) {
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-E[u]));
+        out[u] = gk.lambda * e;
+    }
 }
 
 // integer division of small non-negative ints through fp32 (exact while a < 2^22 and the quotient's fractional part
@@ -506,12 +511,10 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 192 ? PK_MINB192 : BOUND <= 2
             rec->off0 = o0;
             rec->off1 = o1;
             rec->st_off = rowoff[r] - (gstB[c * npc + p] - clsB[c]);       // + column position in the class = stored cell
-            if (sizeof(T) == 8) {                  // fp64: lengths in units that make the squared distance the exponent
-                rec->a0 *= (T)a.bscale;
-                rec->a1 *= (T)a.bscale;
-            }
+            rec->a0 *= (T)a.bscale;                // lengths in units that make the squared distance the exponent
+            rec->a1 *= (T)a.bscale;
         }
-        if (sizeof(T) == 8) {
+        {
             T *b0w = const_cast<T *>(b0p), *b1w = const_cast<T *>(b1p);
             const int nB = hB[0];
             for (int c = tid; c < nB; c += NT) {
@@ -1160,6 +1163,8 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
         std::memcpy(&eb, &emax, 8);
         args.clamp_hi = (int)(eb >> 32) - 1;
         args.bscale = std::sqrt(64.0 / (std::log(2.0) * p->gauss));
+    } else {
+        args.bscale = std::sqrt(1.0 / (std::log(2.0) * p->gauss));       // fp32: exponent in octaves
     }
 
     // Upper bound of the stored C cells over all pairs: row i keeps one cell per column of its own (class, parent code)
