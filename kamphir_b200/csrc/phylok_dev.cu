@@ -9,13 +9,16 @@
 //
 // One CTA evaluates one tree pair (persistent CTAs pull pairs from an atomic work counter).  The row tree's ROW part and
 // the column tree's COLUMN part are staged into shared memory with one TMA bulk copy each (cp.async.bulk + mbarrier).
-// Rows are sorted by (class, level, post-order), columns by (class, parent code, post-order): the matched cells of a
-// pair form one dense cntA[c] x cntB[c] rectangle per production class c, level L of the wavefront is a contiguous row
-// range of each rectangle, and the cells of a row that are ever read again (same parent code) are one contiguous
-// column group -- only that group is stored (R ~ 0.39 M cells).  Thread t owns column t of every rectangle
-// (column-stationary), keeps that node's data in registers while it walks the rows of a (level, class) rectangle four
-// at a time, and all warps meet at one __syncthreads per level (child cells live in strictly lower levels).
-// Stored cells live in shared memory for tiny pairs, otherwise in a per-CTA slab in HBM that stays mostly L2-resident:
+// Rows are sorted by (class, level, post-order), columns by (class, parent code, ancestors' parent codes, post-order):
+// the matched cells of a pair form one dense cntA[c] x cntB[c] rectangle per production class c, level L of the
+// wavefront is a contiguous row range of each rectangle, and the cells of a row that are ever read again (same parent
+// code) are one contiguous column group -- only that group is stored (R ~ 0.39 M cells).  Thread t owns column t of
+// every rectangle (column-stationary; labelled trees deal the 32-column chunks of a level's many narrow rectangles to
+// the warps instead), keeps that node's data in registers while it walks the rows of a (level, class) rectangle two (or
+// four) at a time, and all warps meet at one __syncthreads per level (child cells live in strictly lower levels).
+// The branch lengths are pre-scaled per pair so that the squared distance is the exponent of the Gaussian in binary
+// octaves (fp64: table + degree-4 polynomial + integer exponent add, 8 fp64 instructions; fp32: one MUFU.EX2).
+// Stored cells live in shared memory for tiny pairs, otherwise in a per-CTA slab in HBM that stays L1/L2-resident:
 // coalesced group writes, software-pipelined child-cell gathers.
 // No tensor cores (not a contraction), no CPU fallback.
 #include <cuda_runtime.h>
