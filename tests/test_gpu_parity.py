@@ -259,6 +259,44 @@ def test_gram_matrix(precision):
         assert abs(raw[i, j] - c_oracle.kernel(orac[i], orac[j], 0.2, 2.0)) <= TOL[precision] * raw[i, j]
 
 
+def test_gram_at_headline_size_properties():
+    """configs[3] shape at a size the oracle still samples quickly: 160 x 500-tip trees (12 880 DPs): symmetry, unit
+    diagonal, normalised = raw / sqrt(diag diag), a Cauchy-Schwarz bound, and sampled entries against the C oracle."""
+    nwk = synth.tree_set(160, 500, 3000, "mixed")
+    flats = FlatTree.many_from_newick("\n".join(nwk))
+    pk = PhyloKernel(**KAM)
+    raw = pk.gram(flats, normalised=False)
+    nrm = pk.gram(flats, normalised=True)
+    assert np.array_equal(raw, raw.T) and np.array_equal(nrm, nrm.T)
+    assert np.allclose(np.diag(nrm), 1.0, rtol=0, atol=1e-12)
+    d = np.sqrt(np.diag(raw))
+    assert rel(nrm, raw / np.outer(d, d)) <= 1e-12
+    assert np.all(nrm > 0) and np.all(nrm <= 1 + 1e-12)          # K is a positive-definite kernel: |K_ij| <= sqrt(K_ii K_jj)
+    assert get_context().last_stats()["path"] == "hbm"
+    rng = np.random.default_rng(1)
+    for i, j in rng.integers(0, 160, size=(12, 2)):
+        a, b = oracle_flat(nwk[i]), oracle_flat(nwk[j])
+        assert abs(raw[i, j] - c_oracle.kernel(a, b, 0.2, 2.0)) <= 1e-9 * raw[i, j]
+
+
+def test_pangea_size_proposal():
+    """configs[4] shape: 2000-tip replicates against a 2000-tip target through the one-call path; k and denom against the
+    C oracle, the normalised score from them as kamphir.py:300 defines it, the mean as kamphir.py:450."""
+    obs = synth.kingman_newick(2000, 2000)
+    sims = [synth.kingman_newick(2000, 2100 + i) for i in range(6)]
+    pk = PhyloKernel(normalize="mean", **KAM)
+    res = pk.score_batch(obs, [s.encode() for s in sims], use_kcoal=True)
+    fo = oracle_flat(obs)
+    ref = c_oracle.kernel(fo, fo, 0.2, 2.0)
+    assert rel(res["ref_denom"], ref) < 1e-12
+    for s, k, dn, kh in zip(sims, res["k"], res["denom"], res["knorm"]):
+        fs = oracle_flat(s)
+        want_k, want_d = c_oracle.kernel(fo, fs, 0.2, 2.0), c_oracle.kernel(fs, fs, 0.2, 2.0)
+        assert abs(k - want_k) <= 1e-9 * want_k and abs(dn - want_d) <= 1e-9 * want_d
+        assert abs(kh - np.exp(np.log(want_k) - 0.5 * (np.log(ref) + np.log(want_d)))) <= 1e-9
+    assert res["mean_score"] == pytest.approx(float(np.mean(res["knorm"] * res["kcoal"])), rel=1e-14)
+
+
 def test_gram_parts_tile_the_matrix():
     """The sharded form: parts are disjoint, cover the upper triangle, and agree with the one-part result."""
     import ctypes
