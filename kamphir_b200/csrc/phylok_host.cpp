@@ -303,6 +303,50 @@ int parse_one(const char *text, size_t b, size_t e, RawTree &t, bool ladderize, 
         } else if (ch == ':') {
             size_t j = i + 1;
             while (j < e && text[j] == ' ') ++j;
+            // one pass over the usual form digits[.digits][e[+-]digits] (see parse_length: exact when the mantissa has at
+            // most 19 digits and the power of ten is within 10^22); anything else is delimited and handed to parse_length
+            {
+                static const double kP10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                                1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+                const char *q = text + j, *const end = text + e;
+                uint64_t m = 0;
+                int digits = 0, frac = 0, ex = 0;
+                bool any = false, ok = true;
+                while (q < end && (unsigned)(*q - '0') < 10u) {
+                    if (m || *q != '0') { ++digits; m = m * 10 + (unsigned)(*q - '0'); }
+                    any = true;
+                    ++q;
+                }
+                if (q < end && *q == '.') {
+                    ++q;
+                    while (q < end && (unsigned)(*q - '0') < 10u) {
+                        if (m || *q != '0') { ++digits; m = m * 10 + (unsigned)(*q - '0'); }
+                        any = true;
+                        ++frac;
+                        ++q;
+                    }
+                }
+                if (any && q < end && (*q == 'e' || *q == 'E')) {
+                    const char *q0 = q++;
+                    bool eneg = false;
+                    if (q < end && (*q == '+' || *q == '-')) { eneg = *q == '-'; ++q; }
+                    if (q < end && (unsigned)(*q - '0') < 10u) {
+                        while (q < end && (unsigned)(*q - '0') < 10u && ex < 100000) ex = ex * 10 + (*q++ - '0');
+                        if (eneg) ex = -ex;
+                    } else {
+                        q = q0;
+                        ok = false;
+                    }
+                }
+                ex -= frac;
+                if (ok && any && digits <= 19 && m < ((uint64_t)1 << 53) && ex >= -22 && ex <= 22 &&
+                    (q == end || is_token_end(*q))) {
+                    const double v = (double)m;
+                    nd[cur].bl = ex < 0 ? v / kP10[-ex] : v * kP10[ex];
+                    i = (size_t)(q - text);
+                    continue;
+                }
+            }
             size_t k = j;
             while (k < e && !is_token_end(text[k])) ++k;
             size_t s = j;
