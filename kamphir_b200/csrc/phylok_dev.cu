@@ -266,13 +266,37 @@ __device__ __forceinline__ int4 lds_int4(const int4 *p) {     // always one LDS.
     return v;
 }
 
+// PK_OVERRUN (HBM slabs only): the software pipeline always reads the NEXT U row records and issues their gathers, also
+// when they lie past the rectangle -- no pointer clamp in the loop, and the last 1..U-1 rows of a rectangle find their
+// child cells already in flight.  What makes it safe: the records after a rectangle are other rows of the same staged
+// tree (patched, so their offsets are real stored-row offsets), U never-matching records follow the last row (written
+// after staging), and the slab has a slack of the largest column group, so offset + rank stays inside the slab; the
+// values fetched for rows beyond the rectangle are never used.
+#ifndef PK_OVERRUN
+#define PK_OVERRUN 1
+#endif
+#ifndef PK_OPAQUE_Q
+#define PK_OPAQUE_Q 1
+#endif
+#ifndef PK_FMA_SUM
+#define PK_FMA_SUM 1
+#endif
+#ifndef PK_FENCE_ALL
+#define PK_FENCE_ALL 0
+#endif
+#define PK_PAD_RECORDS 4      // >= the largest U
 // child cell of slot 0 / 1: the stored cell when the children's classes agree, else cell 1 (= 1, productions differ)
 #define PK_GATHER0(q) C.ld((((q).w ^ qb0) & 0xff) == 0 ? (q).x + kb0 : 1)
 #define PK_GATHER1(q) C.ld((((q).w ^ qb1) & 0xff00) == 0 ? (q).y + kb1 : 1)
-template <typename T, bool CSMEM, bool G0, bool G1, int U, bool FENCE>
+template <typename T, bool CSMEM, bool G0, bool G1, int U, bool FENCE, bool OVRQ>
 __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0, T b1, int cb0, int cb1, int pkey,
                                      const Cells<T, CSMEM> &C, const GaussK<T> &gk, T sigma, T tipf) {
-    const int qb0 = (unsigned)cb0 >> 24, kb0 = cb0 & 0xffffff;             // child class + 1 (0 = tip), rank in its group
+    constexpr bool OVR = OVRQ && !CSMEM;         // the prefetch may run past the rectangle (see PK_OVERRUN)
+    int qb0 = (unsigned)cb0 >> 24;                                         // child class + 1 (0 = tip)
+#if PK_OPAQUE_Q
+    asm("" : "+r"(qb0));      // hide the value range: the class test of slot 0 stays one LOP3 with a predicate result
+#endif
+    const int kb0 = cb0 & 0xffffff;                                        // rank in its group
     const int qb1 = ((unsigned)cb1 >> 24) << 8, kb1 = cb1 & 0xffffff;      // ... aligned with byte 1 of rec.packed
     T cf = (T)1;                                                           // factor of the slots that are tips in every row
     if (!G0) cf = qb0 == 0 ? tipf : (T)1;
@@ -298,7 +322,7 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
             g[u] = G0 ? (G1 ? f0[u] * f1[u] : f0[u] * cf) : (G1 ? f1[u] * cf : cf);
         }
         if (G0 || G1) {   // always prefetch (the last group re-reads itself: no join, no register copies)
-            const int4 *np = rr + 2 * U <= rows ? ip + 2 * U : ip;
+            const int4 *np = OVR || rr + 2 * U <= rows ? ip + 2 * U : ip;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int4 q = lds_int4(np + 2 * u + 1);
@@ -313,21 +337,28 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
         pk_gauss<U>(x, ev, gk);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
+#if PK_FMA_SUM
+            if (((rp[u].packed ^ pkey) & 0xff0000) == 0) C.st(rp[u].st_off + jb, fma(ev[u], g[u], sigma));
+            part = fma(ev[u], g[u], part);
+#else
             const T v = ev[u] * g[u];
             if (((rp[u].packed ^ pkey) & 0xff0000) == 0) C.st(rp[u].st_off + jb, v + sigma);
             part += v;
+#endif
         }
     }
-    // the last 1..U-1 rows: all their gathers first (one exposed round trip, not one per row)
+    // the last 1..U-1 rows: all their gathers first (one exposed round trip, not one per row); with OVR the last group of
+    // the loop above has already fetched them
     const int rem = rows - rr;
     if (U > 1 && rem > 0) {
-        T g0[U > 1 ? U - 1 : 1], g1[U > 1 ? U - 1 : 1];
+        if ((G0 || G1) && !(OVR && rr > 0)) {
 #pragma unroll
-        for (int u = 0; u < U - 1; ++u) {
-            if (u < rem) {
-                const int4 q = lds_int4(ip + 2 * u + 1);
-                if (G0) g0[u] = PK_GATHER0(q);
-                if (G1) g1[u] = PK_GATHER1(q);
+            for (int u = 0; u < U - 1; ++u) {
+                if (u < rem) {
+                    const int4 q = lds_int4(ip + 2 * u + 1);
+                    if (G0) f0[u] = PK_GATHER0(q);
+                    if (G1) f1[u] = PK_GATHER1(q);
+                }
             }
         }
 #pragma unroll
@@ -336,10 +367,15 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
                 const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
                 T x1[1] = {fma(d1, d1, d0 * d0)}, e1[1];
                 pk_gauss<1>(x1, e1, gk);
-                const T g = G0 ? (G1 ? g0[u] * g1[u] : g0[u] * cf) : (G1 ? g1[u] * cf : cf);
+                const T g = G0 ? (G1 ? f0[u] * f1[u] : f0[u] * cf) : (G1 ? f1[u] * cf : cf);
+#if PK_FMA_SUM
+                if (((rp[u].packed ^ pkey) & 0xff0000) == 0) C.st(rp[u].st_off + jb, fma(e1[0], g, sigma));
+                part = fma(e1[0], g, part);
+#else
                 const T v = e1[0] * g;
                 if (((rp[u].packed ^ pkey) & 0xff0000) == 0) C.st(rp[u].st_off + jb, v + sigma);
                 part += v;
+#endif
             }
         }
     }
@@ -369,20 +405,29 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
 // otherwise thread t owns column t of every rectangle and the rectangles of a level run one after the other.
 template <typename T, bool CSMEM, int BOUND, bool DEAL>     // BOUND: upper bound of the CTA size (sets the register budget)
 #ifndef PK_MINB192
-#define PK_MINB192 4
+#define PK_MINB192 5
+#endif
+#ifndef PK_MINB192_DEAL
+#define PK_MINB192_DEAL 4
 #endif
 #ifndef PK_MINB192_F32
 #define PK_MINB192_F32 5
 #endif
-// resident CTAs per SM the register budget is set for: fp64, <= 192 threads: 4 (80 registers); fp32 needs fewer registers
-// per value and no exponent table, 5 CTAs of 64 registers run 6 % faster than 4 of 80
-__global__ void __launch_bounds__(BOUND, (BOUND <= 192 ? (sizeof(T) == 4 ? PK_MINB192_F32 : PK_MINB192)
+// resident CTAs per SM the register budget is set for.  <= 64 threads (100-tip trees): shared memory allows 12 (fp64,
+// 80 registers) / 16 (fp32, 64 registers).  <= 192 threads: 5 CTAs of 64 registers (fp64 at 500 tips: 460 Gcells/s
+// against 452 for 4 CTAs of 80 registers, now that a cell takes 10 % fewer instructions; labelled fp64 stays at 4: its
+// chunk-dealing loop spills at 64 registers).
+__global__ void __launch_bounds__(BOUND, (BOUND <= 64    ? (sizeof(T) == 4 ? 16 : 12)
+                                          : BOUND <= 192 ? (sizeof(T) == 4 ? PK_MINB192_F32 : DEAL ? PK_MINB192_DEAL : PK_MINB192)
                                           : BOUND <= 224 ? 4 : BOUND <= 256 ? PK_MINB : BOUND <= 384 ? 2 : 1))
     pk_dp_kernel(const DpArgs a) {
     const int NT = blockDim.x, NW = NT >> 5;       // any multiple of 32 up to BOUND
     // rows in flight per lane: 2 where several CTAs share an SM (more, lighter warps hide the latencies better: measured
     // 445 vs 410 Gcells/s at 500 tips), 4 where one big CTA owns the SM (2000 tips: 417 vs 363)
     constexpr int U = BOUND <= PK_U2_BOUND ? PK_USMALL : PK_UNROLL;
+    // where the unclamped prefetch pays (measured at 500 tips: fp32 744 -> 806 Gcells/s, labelled fp64 283 -> 297) and where
+    // it does not (unlabelled fp64: ptxas then issues the gathers late, 452 -> 411)
+    constexpr bool OVRQ = PK_OVERRUN != 0 && (PK_OVERRUN == 2 || sizeof(T) == 4 || DEAL);
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ long long s_work[2];
@@ -457,12 +502,19 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 192 ? (sizeof(T) == 4 ? PK_MI
 
         // ---- stage both node blocks with TMA bulk copies ---------------------------------------
         if (tid == 0) {
+            // the staging buffers were last written through the generic proxy (record patch, length scale, pad records)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(&s_bar, bytesR + bytesC);
             tma_bulk_g2s(sA, srcR, bytesR, &s_bar);
             tma_bulk_g2s(sB, srcC, bytesC, &s_bar);
         }
         mbar_wait(&s_bar, parity);
         parity ^= 1;
+        if (OVRQ && !CSMEM && tid < PK_PAD_RECORDS) {     // never-matching records after the last row (see PK_OVERRUN)
+            int4 *padrec = reinterpret_cast<int4 *>(sA + bytesR) + 2 * tid;
+            padrec[0] = make_int4(0, 0, 0, 0);
+            padrec[1] = make_int4(0, 0, 0, 0xffff);
+        }
 
         const int *hA = reinterpret_cast<const int *>(sA);
         const int *hB = reinterpret_cast<const int *>(sB);
@@ -567,19 +619,19 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 192 ? (sizeof(T) == 4 ? PK_MI
         T part;                                                                                                       \
         switch ((D).flags & (512 | 1024)) {               /* bit 9 / 10: slot 0 / 1 is a tip in every row of the class */ \
         case 512 | 1024:                                                                                              \
-            part = pk_rect<T, CSMEM, false, false, U, DEAL>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,   \
+            part = pk_rect<T, CSMEM, false, false, U, DEAL || PK_FENCE_ALL, OVRQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,   \
                                                             cells, gk, sigma, tipf);                                  \
             break;                                                                                                    \
         case 512:                                                                                                     \
-            part = pk_rect<T, CSMEM, false, true, U, DEAL>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,    \
+            part = pk_rect<T, CSMEM, false, true, U, DEAL || PK_FENCE_ALL, OVRQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,    \
                                                            cells, gk, sigma, tipf);                                   \
             break;                                                                                                    \
         case 1024:                                                                                                    \
-            part = pk_rect<T, CSMEM, true, false, U, DEAL>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,    \
+            part = pk_rect<T, CSMEM, true, false, U, DEAL || PK_FENCE_ALL, OVRQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,    \
                                                            cells, gk, sigma, tipf);                                   \
             break;                                                                                                    \
         default:                                                                                                      \
-            part = pk_rect<T, CSMEM, true, true, U, DEAL>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,     \
+            part = pk_rect<T, CSMEM, true, true, U, DEAL || PK_FENCE_ALL, OVRQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,     \
                                                           cells, gk, sigma, tipf);                                    \
         }                                                                                                             \
         acc += (double)part;                                                                                          \
@@ -1111,10 +1163,11 @@ static cudaError_t occupancy_t(pk_ctx *ctx, int nt, int smem, int *blocks) {
     return e;
 }
 
-// register budgets: <= 224 threads: 72 registers (4 CTAs of 7 warps per SM), <= 256: 80 (3 CTAs), <= 384: 80 (2 CTAs),
-// <= 512: 128, <= 768: 80, else 64 (one CTA per SM)
+// register budgets: <= 64 threads: 80 registers (fp32: 64), <= 192: 64 (5 CTAs per SM; labelled fp64 80), <= 224: 72
+// (4 CTAs of 7 warps), <= 256: 80 (3 CTAs), <= 384: 80 (2 CTAs), <= 512: 128, <= 768: 80, else 64 (one CTA per SM)
 #define PK_DISPATCH_NT(FN, TT, CS, DL, ...)                                                     \
-    (nt <= 192   ? FN<TT, CS, 192, DL>(__VA_ARGS__)                                             \
+    (nt <= 64    ? FN<TT, CS, 64, DL>(__VA_ARGS__)                                              \
+     : nt <= 192 ? FN<TT, CS, 192, DL>(__VA_ARGS__)                                           \
      : nt <= 224 ? FN<TT, CS, 224, DL>(__VA_ARGS__)                                             \
      : nt <= 256 ? FN<TT, CS, 256, DL>(__VA_ARGS__)                                             \
      : nt <= 384 ? FN<TT, CS, 384, DL>(__VA_ARGS__)                                             \
@@ -1192,7 +1245,7 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
             }
         maxM += 2;   // cell 0 (tip x tip factor) and cell 1 (no-match factor) precede the rows
     }
-    const int region_r = (std::max(fa->max_rowpart, fb->max_rowpart) + 127) & ~127;
+    const int region_r = (std::max(fa->max_rowpart, fb->max_rowpart) + 32 * PK_PAD_RECORDS + 127) & ~127;
     const int region_c = (std::max(fa->max_colpart, fb->max_colpart) + 127) & ~127;
     const int max_n = std::max(fa->max_n, fb->max_n);
     const int rowinfo = ((max_n * 4) + 127) & ~127;                          // row offsets
@@ -1244,7 +1297,10 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
     long long grid_ll = std::min<long long>(args.total, (long long)per_sm * ctx->sm_count);
     int grid = (int)std::max(1ll, grid_ll);
     if (!csmem) {
-        args.slab_elems = (((maxM * (long long)w) + 255) & ~255ll) / (long long)w;
+        long long slack = 0;          // PK_OVERRUN: offset of any stored row + rank in any column group stays inside
+        if (PK_OVERRUN)
+            for (size_t g = 0; g < fa->max_gcnt.size(); ++g) slack = std::max<long long>(slack, std::max(fa->max_gcnt[g], fb->max_gcnt[g]));
+        args.slab_elems = ((((maxM + slack) * (long long)w) + 255) & ~255ll) / (long long)w;
         int rc = ensure_scratch(ctx, (size_t)grid * (size_t)args.slab_elems * w);
         if (rc) return rc;
         args.scratch = ctx->d_scratch;
