@@ -278,9 +278,6 @@ __device__ __forceinline__ int4 lds_int4(const int4 *p) {     // always one LDS.
 #ifndef PK_OPAQUE_Q
 #define PK_OPAQUE_Q 1
 #endif
-#ifndef PK_FMA_SUM
-#define PK_FMA_SUM 1
-#endif
 #ifndef PK_FENCE_ALL
 #define PK_FENCE_ALL 0
 #endif
@@ -303,6 +300,7 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
     if (!G1) cf *= qb1 == 0 ? tipf : (T)1;
     T part = (T)0;
     T f0[U], f1[U];
+    const unsigned am = FENCE ? __activemask() : 0u;     // the lanes of this warp that own a column of the rectangle
     int rr = 0;
     const int4 *ip = reinterpret_cast<const int4 *>(rp);                   // ip[2 r + 1] = {off0, off1, st_off, packed}
     if ((G0 || G1) && U <= rows) {
@@ -330,21 +328,18 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
                 if (G1) f1[u] = PK_GATHER1(q);
             }
             // ptxas is free to sink the gathers below the Gaussians, and whether it does depends on unrelated code around
-            // the loop (375 instead of 445 Gcells/s when the chunk-dealing level loop was introduced).  Memory operations
-            // do not cross a warp barrier: FENCE pins the gathers here (413; costs 2 % where ptxas behaves by itself).
-            if (FENCE) __syncwarp(__activemask());
+            // the loop and on the register budget (375 instead of 445 Gcells/s when the chunk-dealing level loop was
+            // introduced).  Memory operations do not cross a warp barrier: FENCE pins the gathers here (costs 2-4 % where
+            // ptxas behaves by itself).  Measured and dropped: touching the gathered factors only after the Gaussian
+            // (v = (e * f0) * f1) with the next gathers issued after that -- ptxas pairs each row's use with its own
+            // Gaussian, the distance from gather to first use stays ~30 instructions (449 against 460).
+            if (FENCE) __syncwarp(am);
         }
         pk_gauss<U>(x, ev, gk);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-#if PK_FMA_SUM
+        for (int u = 0; u < U; ++u) {     // e * g feeds two FMAs: the stored cell sigma + C and the running sum
             if (((rp[u].packed ^ pkey) & 0xff0000) == 0) C.st(rp[u].st_off + jb, fma(ev[u], g[u], sigma));
             part = fma(ev[u], g[u], part);
-#else
-            const T v = ev[u] * g[u];
-            if (((rp[u].packed ^ pkey) & 0xff0000) == 0) C.st(rp[u].st_off + jb, v + sigma);
-            part += v;
-#endif
         }
     }
     // the last 1..U-1 rows: all their gathers first (one exposed round trip, not one per row); with OVR the last group of
@@ -368,14 +363,8 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
                 T x1[1] = {fma(d1, d1, d0 * d0)}, e1[1];
                 pk_gauss<1>(x1, e1, gk);
                 const T g = G0 ? (G1 ? f0[u] * f1[u] : f0[u] * cf) : (G1 ? f1[u] * cf : cf);
-#if PK_FMA_SUM
                 if (((rp[u].packed ^ pkey) & 0xff0000) == 0) C.st(rp[u].st_off + jb, fma(e1[0], g, sigma));
                 part = fma(e1[0], g, part);
-#else
-                const T v = e1[0] * g;
-                if (((rp[u].packed ^ pkey) & 0xff0000) == 0) C.st(rp[u].st_off + jb, v + sigma);
-                part += v;
-#endif
             }
         }
     }
