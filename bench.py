@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
     ap.add_argument("--tile", type=int, default=32)
     ap.add_argument("--gather", default="p2p", choices=["p2p", "allreduce"])
-    ap.add_argument("--cpu-sample", type=int, default=32, help="DPs in the single-process cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=256, help="DPs in the single-process cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-sample", type=int, default=64)
     return ap.parse_args()
@@ -164,7 +164,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = max(4 * cores, 32)
+    per_step = max(32 * cores, 256)      # ~1 s of work per step on every core: the pool's dispatch cost is negligible
     newicks = make_trees(min(args.trees, 256), args.tips)
     n = len(newicks)
     steps = args.warmup + args.steps
