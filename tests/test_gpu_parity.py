@@ -106,6 +106,35 @@ def test_every_cta_shape_gives_the_same_answer(threads):
     assert rel(a, base) < 1e-13 and rel(b, base) < 1e-13
 
 
+@pytest.mark.parametrize("precision,states", [(32, 0), (64, 3), (32, 3), (64, 0)])
+def test_small_pairs_after_large_pairs_on_the_same_cta(precision, states):
+    """One resident CTA per SM with the C cells in HBM slabs works through a list that alternates large and small trees:
+    the staged tree of a small pair is followed in shared memory by what the large one left behind, and the unclamped
+    prefetch of the fp32 / labelled kernel variants (PK_OVERRUN) reads the records after a rectangle -- other rows of the
+    same tree, then the never-matching pad records -- and may address the slab's slack.  Results must not depend on it."""
+    sizes = [300, 7, 150, 3, 260, 12, 2, 90, 280, 5, 33, 310]
+    nwk = [synth.kingman_newick(n, 700 + i, states=states) if i % 3 else synth.yule_newick(n, 700 + i, states=states)
+           for i, n in enumerate(sizes)]
+    flats = [FlatTree.from_newick(s, 3, "mean", states) for s in nwk]
+    pk = PhyloKernel(precision=precision, n_states=states, **KAM)
+    pairs = [(i, j) for i in range(len(sizes)) for j in range(len(sizes))] * 3      # 432 work items > resident CTAs
+    get_context().configure(0, 1, 1)
+    got = pk.kernel_batch(flats, flats, pairs)
+    if states:
+        of = [po.prep_kamphir(po.read_newick(s), "mean", po.state_from_name) for s in nwk]
+        want = {}
+        for i, j in set(pairs):
+            if i <= j:
+                want[(i, j)] = want[(j, i)] = po.kernel_arrays_labelled(of[i], of[j], 0.2, 2.0, 1.0)
+        want = np.array([want[p] for p in pairs])
+    else:
+        orac = [oracle_flat(s) for s in nwk]
+        want = np.array([c_oracle.kernel(orac[i], orac[j], 0.2, 2.0, 1.0) for i, j in pairs])
+    assert rel(got, want) < TOL[precision]
+    n = len(sizes) ** 2
+    assert np.array_equal(got[:n], got[n:2 * n]) and np.array_equal(got[:n], got[2 * n:])      # deterministic
+
+
 def test_parameters_sigma_lambda_tau():
     nwk = synth.tree_set(4, 80, 40)
     flats = [FlatTree.from_newick(s) for s in nwk]
