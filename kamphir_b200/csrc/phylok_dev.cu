@@ -717,6 +717,8 @@ struct pk_ctx {
     size_t tmp_bytes = 0;
     void *h_pinned = nullptr;
     size_t pinned_bytes = 0;
+    cudaEvent_t pinned_ev = nullptr;            // recorded behind an async copy out of h_pinned that nobody waits for
+    bool pinned_inflight = false;
     std::vector<std::pair<void *, size_t>> pool;   // device buffers of freed forests, reused by later uploads (all work
                                                    // is ordered on ctx->stream, so reuse needs no extra synchronisation)
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -790,6 +792,7 @@ extern "C" int pk_ctx_create(int device, pk_ctx **out) {
     if (err == cudaSuccess) err = cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * kCounterRing);
     if (err == cudaSuccess) err = cudaEventCreate(&ctx->ev[0]);
     if (err == cudaSuccess) err = cudaEventCreate(&ctx->ev[1]);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&ctx->pinned_ev, cudaEventDisableTiming);
     if (err != cudaSuccess) {
         delete ctx;
         return pk_fail(PK_ERR_CUDA, std::string("pk_ctx_create: ") + cudaGetErrorString(err));
@@ -809,6 +812,7 @@ extern "C" void pk_ctx_destroy(pk_ctx *ctx) {
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
+    if (ctx->pinned_ev) cudaEventDestroy(ctx->pinned_ev);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -882,7 +886,12 @@ static int ensure_tmp(pk_ctx *ctx, size_t bytes) {
     return PK_OK;
 }
 
+// called before every host write into the staging buffer
 static int ensure_pinned(pk_ctx *ctx, size_t bytes) {
+    if (ctx->pinned_inflight) {      // an earlier call left a copy out of the buffer queued (Gram tile list)
+        PK_CUDA(cudaEventSynchronize(ctx->pinned_ev));
+        ctx->pinned_inflight = false;
+    }
     if (bytes <= ctx->pinned_bytes) return PK_OK;
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -935,8 +944,11 @@ static void pool_release(pk_ctx *ctx, void *ptr, size_t bytes) {
 
 // [part_lo, part_hi): the trees this call packs and copies to the device (all of them for a plain upload); the layout,
 // the per-part meta records and the host-side statistics always cover the whole set
+// tail_off != nullptr (transient forests of the host-tree entry points): the pinned staging buffer gets `tail_bytes` more
+// after the forest (at *tail_off, for the caller's pair list and results) and the copy is NOT waited for -- the caller
+// synchronises the stream once, after its own launch; until then it must not touch the staging buffer before *tail_off.
 static int forest_upload_impl(pk_ctx *ctx, const pk_tree *const *trees, int32_t n, int32_t precision, int32_t part_lo,
-                              int32_t part_hi, pk_forest **out) {
+                              int32_t part_hi, pk_forest **out, size_t tail_bytes = 0, size_t *tail_off = nullptr) {
     if (!ctx || !trees || !out) return pk_fail(PK_ERR_INVALID, "null argument");
     if (n < 1) return pk_fail(PK_ERR_INVALID, "empty tree set");
     if (part_lo < 0 || part_hi > n || part_lo > part_hi) return pk_fail(PK_ERR_INVALID, "tree range out of bounds");
@@ -967,11 +979,13 @@ static int forest_upload_impl(pk_ctx *ctx, const pk_tree *const *trees, int32_t 
     f->nint.resize(n);
     f->tree_w.assign(n, 1);
     const size_t meta_bytes = sizeof(int4) * 2 * (size_t)n;
-    rc = ensure_pinned(ctx, total + meta_bytes);
+    const size_t staged = (total + meta_bytes + 255) & ~(size_t)255;
+    rc = ensure_pinned(ctx, staged + tail_bytes);
     if (rc) {
         delete f;
         return rc;
     }
+    if (tail_off) *tail_off = staged;
     unsigned char *h = static_cast<unsigned char *>(ctx->h_pinned);
     int4 *hmeta = reinterpret_cast<int4 *>(h + total);
     std::vector<size_t> offs((size_t)n + 1, 0);
@@ -1041,7 +1055,7 @@ static int forest_upload_impl(pk_ctx *ctx, const pk_tree *const *trees, int32_t 
         }
         std::copy(t.hist.begin(), t.hist.end(), f->hist.begin() + (size_t)i * t.hist.size());
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // the pinned staging buffer is reused
+    if (e == cudaSuccess && !tail_off) e = cudaStreamSynchronize(ctx->stream);   // the pinned staging buffer is reused
     if (e != cudaSuccess) {
         if (f->d_blocks) cudaFree(f->d_blocks);
         delete f;
@@ -1355,20 +1369,29 @@ static int kernel_pairs_impl(pk_ctx *ctx, const pk_tree *const *A, int32_t nA, c
     static const bool trace = std::getenv("PK_TRACE") != nullptr;
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = trace ? now() : 0.0;
-    rc = pk_forest_upload(ctx, A, nA, prec, &fa);
+    const size_t pb = sizeof(int32_t) * 2 * (size_t)npairs, ob = sizeof(double) * (size_t)npairs;
+    const size_t pb_al = (pb + 255) & ~(size_t)255;
+    const bool same = (A == B && nA == nB);
+    // one tree set (a proposal's replicates + the observed tree): its upload is not waited for, the pair list and the
+    // results live behind it in the staging buffer and the stream is synchronised once, at the end
+    size_t tail = 0;
+    bool deferred = false;
+    if (same) {
+        rc = forest_upload_impl(ctx, A, nA, prec, 0, nA, &fa, pb_al + ob, &tail);
+        deferred = rc == PK_OK;
+    } else {
+        rc = pk_forest_upload(ctx, A, nA, prec, &fa);
+    }
     if (rc) return rc;
     if (trace) std::fprintf(stderr, "pk_kernel_pairs: forest upload %.0f us\n", 1e6 * (now() - t0));
-    const bool same = (A == B && nA == nB);
     if (same) fb = fa;
     else rc = pk_forest_upload(ctx, B, nB, prec, &fb);
     if (rc == PK_OK) {
-        const size_t pb = sizeof(int32_t) * 2 * (size_t)npairs, ob = sizeof(double) * (size_t)npairs;
-        const size_t pb_al = (pb + 255) & ~(size_t)255;
         rc = ensure_tmp(ctx, pb_al + ob);
-        if (rc == PK_OK) rc = ensure_pinned(ctx, pb_al + ob);
+        if (rc == PK_OK && !same) rc = ensure_pinned(ctx, pb_al + ob);
         if (rc == PK_OK) {
             unsigned char *d = static_cast<unsigned char *>(ctx->d_tmp);
-            unsigned char *h = static_cast<unsigned char *>(ctx->h_pinned);
+            unsigned char *h = static_cast<unsigned char *>(ctx->h_pinned) + tail;
             std::memcpy(h, pairs, pb);
             cudaError_t e = cudaMemcpyAsync(d, h, pb, cudaMemcpyHostToDevice, ctx->stream);
             if (e != cudaSuccess) rc = pk_fail(PK_ERR_CUDA, cudaGetErrorString(e));
@@ -1387,6 +1410,7 @@ static int kernel_pairs_impl(pk_ctx *ctx, const pk_tree *const *A, int32_t nA, c
         }
     }
     std::string keep = rc ? std::string(pk_last_error()) : std::string();
+    if (rc && deferred) cudaStreamSynchronize(ctx->stream);      // failed before the final wait: the staging buffer may be in flight
     if (fb && fb != fa) pk_forest_free(fb);
     pk_forest_free(fa);
     if (rc) pk_set_error(keep);
@@ -1454,17 +1478,31 @@ extern "C" int pk_score_newick_batch(pk_ctx *ctx, const pk_tree *obs, const char
     std::vector<double> khat((size_t)n), kc;
     const bool use_kcoal = !std::isnan(kadj);
     // kcoal is host work (sorting the replicates' node heights) that does not depend on the DP: it runs on the worker
-    // pool while the kernel does (after the forest is packed and uploaded, which uses the same pool)
+    // pool while the kernel does (after the forest is packed and uploaded, which uses the same pool).  After that nothing
+    // reads the replicates' host trees any more; they are destroyed in the same window, spread over the pool (a tree is
+    // ~16 heap blocks: 116 us on one thread for 100 trees, a seventh of a configs[1] proposal).
     int rc_kcoal = PK_OK;
     std::string err_kcoal;
     bool kcoal_done = false;
-    std::function<void()> overlap = [&]() {
-        kc.resize((size_t)n);
-        rc_kcoal = pk_kcoal_batch(trees, n, obs, kc.data());
-        if (rc_kcoal) err_kcoal = pk_last_error();
-        kcoal_done = true;
+    auto free_trees = [&]() {
+        if (!trees) return;
+        const int workers = std::max(1, std::min(std::min(pk_host_threads(), 16), n / 8));
+        pk_parallel(workers, [&](int wk) {
+            for (int32_t s = wk; s < n; s += workers) pk_tree_free(trees[s]);
+        });
+        pk_tree_array_free(trees);
+        trees = nullptr;
     };
-    rc = score_batch_impl(ctx, obs, trees, n, params, ref_denom, out_k, out_denom, khat.data(), use_kcoal ? &overlap : nullptr);
+    std::function<void()> overlap = [&]() {
+        if (use_kcoal) {
+            kc.resize((size_t)n);
+            rc_kcoal = pk_kcoal_batch(trees, n, obs, kc.data());
+            if (rc_kcoal) err_kcoal = pk_last_error();
+            kcoal_done = true;
+        }
+        free_trees();
+    };
+    rc = score_batch_impl(ctx, obs, trees, n, params, ref_denom, out_k, out_denom, khat.data(), &overlap);
     const double t2 = trace ? now() : 0.0;
     if (rc == PK_OK && use_kcoal) {
         if (!kcoal_done) overlap();
@@ -1483,8 +1521,7 @@ extern "C" int pk_score_newick_batch(pk_ctx *ctx, const pk_tree *obs, const char
     }
     const double t3 = trace ? now() : 0.0;
     std::string keep = rc ? std::string(pk_last_error()) : std::string();
-    for (int32_t s = 0; s < n; ++s) pk_tree_free(trees[s]);
-    pk_tree_array_free(trees);
+    free_trees();      // only if the call failed before the overlap window
     if (trace)
         std::fprintf(stderr, "pk_score_newick_batch: flatten %.0f us, score_batch %.0f us, kcoal+scores %.0f us, free %.0f us\n",
                      1e6 * (t1 - t0), 1e6 * (t2 - t1), 1e6 * (t3 - t2), 1e6 * (now() - t3));
@@ -1572,6 +1609,8 @@ extern "C" int pk_forest_gram_part(pk_ctx *ctx, const pk_forest *f, const pk_par
     if (rc) return rc;
     std::memcpy(ctx->h_pinned, tiles.data(), tb);
     PK_CUDA(cudaMemcpyAsync(ctx->d_tmp, ctx->h_pinned, tb, cudaMemcpyHostToDevice, ctx->stream));
+    PK_CUDA(cudaEventRecord(ctx->pinned_ev, ctx->stream));      // the launch is not waited for: the next writer of h_pinned is
+    ctx->pinned_inflight = true;
     int shift = 0;
     while ((1 << shift) < tile) ++shift;
     DpArgs args;
