@@ -378,7 +378,7 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
 #define PK_UNROLL 4
 #endif
 #ifndef PK_U2_BOUND
-#define PK_U2_BOUND 256
+#define PK_U2_BOUND 352
 #endif
 #ifndef PK_USMALL
 #define PK_USMALL 2
@@ -411,13 +411,15 @@ template <typename T, bool CSMEM, int BOUND, bool DEAL>     // BOUND: upper boun
 // chunk-dealing loop spills at 64 registers).
 __global__ void __launch_bounds__(BOUND, (BOUND <= 64    ? (sizeof(T) == 4 ? 16 : 12)
                                           : BOUND <= 192 ? (sizeof(T) == 4 ? PK_MINB192_F32 : DEAL ? PK_MINB192_DEAL : PK_MINB192)
-                                          : BOUND <= 224 ? 4 : BOUND <= 256 ? PK_MINB : BOUND <= 384 ? 2 : BOUND <= 512 ? PK_MINB512 : 1))
+                                          : BOUND <= 224 ? 4 : BOUND <= 256 ? PK_MINB : BOUND <= 352 ? 3 : BOUND <= 384 ? 2 : BOUND <= 512 ? PK_MINB512
+                                          : BOUND <= 576 ? 2 : 1))
     pk_dp_kernel(const DpArgs a) {
     const int NT = blockDim.x, NW = NT >> 5;       // any multiple of 32 up to BOUND
     // rows in flight per lane: 2 where several light CTAs share an SM (more, lighter warps hide the latencies better:
-    // measured 445 vs 410 Gcells/s at 500 tips), 4 for the big CTAs (2000 tips: 417 vs 363).  fp32 keeps 2 up to 512
-    // threads (1300 tips, 2 CTAs of 64 registers per SM: 807 vs 755 Gcells/s; fp64 there: 413 vs 420).
-    constexpr int U = BOUND <= (sizeof(T) == 4 ? 2 * PK_U2_BOUND : PK_U2_BOUND) ? PK_USMALL : PK_UNROLL;
+    // measured 445 vs 410 Gcells/s at 500 tips) and wherever the register budget is tight (576-thread tier, 56 registers:
+    // 432 vs 375 at 1500 tips), 4 for the big CTAs with room (1000 tips, 2 CTAs of 80 registers: 425 vs 397; 2000 tips:
+    // 417 vs 363).  fp32 keeps 2 up to 576 threads (1300 tips: 807 vs 755 Gcells/s).
+    constexpr int U = (sizeof(T) == 4 ? BOUND <= 576 : (BOUND <= PK_U2_BOUND || BOUND == 576)) ? PK_USMALL : PK_UNROLL;
     // where the unclamped prefetch pays (measured at 500 tips: fp32 744 -> 806 Gcells/s, labelled fp64 283 -> 297) and where
     // it does not (unlabelled fp64: ptxas then issues the gathers late, 452 -> 411)
     constexpr bool OVRQ = PK_OVERRUN != 0 && (PK_OVERRUN == 2 || sizeof(T) == 4 || DEAL);
@@ -1171,15 +1173,19 @@ static cudaError_t occupancy_t(pk_ctx *ctx, int nt, int smem, int *blocks) {
 }
 
 // register budgets: <= 64 threads: 80 registers (fp32: 64), <= 192: 64 (5 CTAs per SM; labelled fp64 80), <= 224: 72
-// (4 CTAs of 7 warps), <= 256: 80 (3 CTAs), <= 384: 80 (2 CTAs), <= 512: 64 (2 CTAs; one CTA of 128 registers ran 5 %
+// (4 CTAs of 7 warps), <= 256: 80 (3 CTAs), <= 320: 64 and <= 352: 56 (3 CTAs; 800 tips: 432 Gcells/s against 390 in the 384 tier, 900 tips: 415 against 406),
+// <= 384: 80 (2 CTAs), <= 576: 56 (2 CTAs; 1500 tips: 432 against 378 with one CTA), <= 512: 64 (2 CTAs; one CTA of 128 registers ran 5 %
 // (fp64) / 37 % (fp32) slower at 1300 tips), <= 768: 80, else 64 (one CTA per SM)
 #define PK_DISPATCH_NT(FN, TT, CS, DL, ...)                                                     \
     (nt <= 64    ? FN<TT, CS, 64, DL>(__VA_ARGS__)                                              \
      : nt <= 192 ? FN<TT, CS, 192, DL>(__VA_ARGS__)                                           \
      : nt <= 224 ? FN<TT, CS, 224, DL>(__VA_ARGS__)                                             \
      : nt <= 256 ? FN<TT, CS, 256, DL>(__VA_ARGS__)                                             \
+     : nt <= 320 ? FN<TT, CS, 320, DL>(__VA_ARGS__)                                             \
+     : nt <= 352 ? FN<TT, CS, 352, DL>(__VA_ARGS__)                                             \
      : nt <= 384 ? FN<TT, CS, 384, DL>(__VA_ARGS__)                                             \
      : nt <= 512 ? FN<TT, CS, 512, DL>(__VA_ARGS__)                                             \
+     : nt <= 576 ? FN<TT, CS, 576, DL>(__VA_ARGS__)                                             \
      : nt <= 768 ? FN<TT, CS, 768, DL>(__VA_ARGS__)                                             \
                  : FN<TT, CS, 1024, DL>(__VA_ARGS__))
 #define PK_DISPATCH_CS(FN, TT, DL, ...) \

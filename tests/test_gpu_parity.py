@@ -93,17 +93,21 @@ def test_random_pairs_against_c_oracle(precision, force_hbm):
         assert stats["path"] == ("hbm" if force_hbm == 1 else "smem")
 
 
-@pytest.mark.parametrize("threads", [64, 96, 128, 256, 512, 1024])
+@pytest.mark.parametrize("threads", [32, 64, 96, 128, 192, 224, 256, 320, 352, 384, 512, 576, 768, 1024])   # every kernel tier
 def test_every_cta_shape_gives_the_same_answer(threads):
-    nwk = synth.tree_set(6, 120, 900)
-    flats = [FlatTree.from_newick(s) for s in nwk]
-    pk = PhyloKernel(**KAM)
-    base = pk.kernel_batch(flats)
-    get_context().configure(threads, 0, 0)
-    a = pk.kernel_batch(flats)
-    get_context().configure(threads, 2, 2 if threads <= 256 else 1)
-    b = pk.kernel_batch(flats)
-    assert rel(a, base) < 1e-13 and rel(b, base) < 1e-13
+    """The CTA size selects the kernel instantiation (register budget, rows in flight, resident CTAs); a pair's cells do
+    not depend on it, only the order of the final sum does."""
+    for precision, states in [(64, 0), (32, 0), (64, 2)]:
+        nwk = synth.tree_set(6, 120, 900, "mixed", states, [0.5, 0.5] if states else None)
+        flats = [FlatTree.from_newick(s, 3, "mean", states) for s in nwk]
+        pk = PhyloKernel(precision=precision, n_states=states, **KAM)
+        get_context().configure(0, 0, 0)
+        base = pk.kernel_batch(flats)
+        get_context().configure(threads, 0, 0)
+        a = pk.kernel_batch(flats)
+        get_context().configure(threads, 2, 2 if threads <= 256 else 1)
+        b = pk.kernel_batch(flats)
+        assert rel(a, base) < 1e-13 and rel(b, base) < 1e-13, (precision, states)
 
 
 @pytest.mark.parametrize("precision,states", [(32, 0), (64, 3), (32, 3), (64, 0)])
