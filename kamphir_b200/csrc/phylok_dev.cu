@@ -300,7 +300,6 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
     if (!G1) cf *= qb1 == 0 ? tipf : (T)1;
     T part = (T)0;
     T f0[U], f1[U];
-    const unsigned am = FENCE ? __activemask() : 0u;     // the lanes of this warp that own a column of the rectangle
     int rr = 0;
     const int4 *ip = reinterpret_cast<const int4 *>(rp);                   // ip[2 r + 1] = {off0, off1, st_off, packed}
     if ((G0 || G1) && U <= rows) {
@@ -333,7 +332,10 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
             // ptxas behaves by itself).  Measured and dropped: touching the gathered factors only after the Gaussian
             // (v = (e * f0) * f1) with the next gathers issued after that -- ptxas pairs each row's use with its own
             // Gaussian, the distance from gather to first use stays ~30 instructions (449 against 460).
-            if (FENCE) __syncwarp(am);
+            // The mask is taken here, not once per rectangle: lanes that are not converged at this point (a build with
+            // divergent code in the loop, e.g. PK_DEBUG_BOUNDS) each synchronise with whoever is with them; a mask taken at
+            // the rectangle's entry deadlocked exactly there (labelled trees, one-warp CTA).
+            if (FENCE) __syncwarp(__activemask());
         }
         pk_gauss<U>(x, ev, gk);
 #pragma unroll
@@ -531,7 +533,7 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 64    ? (sizeof(T) == 4 ? 16 
         //      (child productions differ).  A cell (i, j) is only ever read by the cell of the two parents, and only when
         //      i and j have the same parent code; columns are ordered by (class, parent code), so row i stores just the
         //      contiguous column group with its own parent code: R cells per pair instead of M.
-        if (tid < ncls) s_cntB[tid] = clsB[tid + 1] - clsB[tid];
+        for (int c = tid; c < ncls; c += NT) s_cntB[c] = clsB[c + 1] - clsB[c];      // a one-warp CTA has fewer threads than 64 classes
         if (tid == 0) {
             cells.st(0, tipf);       // tip x tip child factor (phyloK2.py:194-196)
             cells.st(1, (T)1);       // factor of a child slot whose productions differ (phyloK2.py:191-192)

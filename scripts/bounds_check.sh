@@ -5,5 +5,7 @@
 set -euo pipefail
 cd "$(dirname "$0")/.."
 PK_DEFS="-DPK_DEBUG_BOUNDS" PK_OUT="$PWD/kamphir_b200/libphylok_dbg.so" bash kamphir_b200/csrc/build.sh
-PK_LIB="$PWD/kamphir_b200/libphylok_dbg.so" python scripts/sanitize_case.py
-PK_LIB="$PWD/kamphir_b200/libphylok_dbg.so" python -m pytest tests -m gpu -x -q
+# every step under its own timeout: a deadlock found this way must not eat the GPU box's time limit
+PK_LIB="$PWD/kamphir_b200/libphylok_dbg.so" timeout 120 python scripts/sanitize_case.py
+PK_LIB="$PWD/kamphir_b200/libphylok_dbg.so" timeout 300 python -m pytest tests -m gpu -x -q
+PK_LIB="$PWD/kamphir_b200/libphylok_dbg.so" timeout 120 python scripts/fuzz_parity.py 60

@@ -451,6 +451,9 @@ def test_labelled_many_classes(S):
         assert rel(got, want) <= TOL[precision]
         raw = pk.gram(flats, normalised=False)
         assert rel(raw, want) <= TOL[precision]
+        get_context().configure(32, 0, 0)          # a one-warp CTA: fewer threads than classes (S >= 5)
+        assert rel(pk.kernel_batch(flats), want) <= TOL[precision]
+        get_context().configure(0, 0, 0)
 
 
 def test_load_trees_from_file_and_compute_matrix(tmp_path):
