@@ -484,6 +484,7 @@ class PhyloKernel(object):
             if use_kcoal:
                 res['kcoal'] = out[3]
                 res['score'] = out[4]
+            self._check_log_domain(res)
             return res
         fs = self.flatten_list(sims, PK_PREP_KAMPHIR, self.normalize)
         n = len(fs)
@@ -494,6 +495,7 @@ class PhyloKernel(object):
         check(_lib.lib().pk_score_batch(self._ctx()._h, fo._h, arr, n, ctypes.byref(p), ctypes.byref(ref),
                                         k.ctypes.data, d.ctypes.data, kh.ctypes.data))
         res = dict(k=k, denom=d, knorm=kh, ref_denom=ref.value)
+        self._check_log_domain(res)
         if use_kcoal:
             kc = np.empty(n)
             check(_lib.lib().pk_kcoal_batch(arr, n, fo._h, kc.ctypes.data))
@@ -503,6 +505,15 @@ class PhyloKernel(object):
         else:
             res['mean_score'] = float(kh.sum() / n)
         return res
+
+    @staticmethod
+    def _check_log_domain(res):
+        """kamphir.py:300 takes math.log of k, ref_denom and tree_denom: a replicate without a single matched node pair
+        (decayFactor 0, or labelled trees that share no production class) is a ValueError there, and here."""
+        bad = np.flatnonzero(~((res['k'] > 0) & (res['denom'] > 0)))
+        if bad.size or not res['ref_denom'] > 0:
+            raise ValueError("math domain error (kamphir.py:300): K = 0 for %s"
+                             % ("replicate %d" % bad[0] if bad.size else "the observed tree"))
 
     def score_batch_sharded(self, obs, sims, rank, world, group=None, ref_denom=None, kadj=None, use_kcoal=False):
         """score_batch over the ranks of a torch.distributed group (one process per GPU): rank r scores every

@@ -29,13 +29,20 @@ def sharded_scores(score_fn, sims, rank, world, group=None, device=None):
     sims = list(sims)
     n = len(sims)
     mine = shard_indices(n, rank, world)
-    res = score_fn([sims[i] for i in mine]) if mine else {}
+    err = None
+    try:
+        res = score_fn([sims[i] for i in mine]) if mine else {}
+    except ValueError as e:      # e.g. K = 0 for one replicate (math.log(0) at kamphir.py:300): every rank must still
+        if world == 1:           # reach the all-gather, then all of them raise
+            raise
+        res, err = {}, str(e)
     if world == 1:
         return res
     import torch
     import torch.distributed as dist
     per = (n + world - 1) // world                       # slots per rank (the last ranks may leave one unused)
-    buf = np.full((len(KEYS) + 1, per), np.nan)
+    buf = np.full((len(KEYS) + 2, per), np.nan)
+    buf[len(KEYS) + 1, 0] = 0.0 if err is None else 1.0
     for r, key in enumerate(KEYS):
         if key in res:
             buf[r, :len(mine)] = res[key]
@@ -46,7 +53,10 @@ def sharded_scores(score_fn, sims, rank, world, group=None, device=None):
     out = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(out, t, group=group)
     full = {}
-    stacked = np.stack([o.cpu().numpy() for o in out])   # [world, keys + 1, per]
+    stacked = np.stack([o.cpu().numpy() for o in out])   # [world, keys + 2, per]
+    failed = [w for w in range(world) if stacked[w, len(KEYS) + 1, 0] != 0.0]
+    if failed:
+        raise ValueError(err if err is not None else "rank %d: a replicate's score is undefined (K = 0)" % failed[0])
     for r, key in enumerate(KEYS):
         col = np.full(n, np.nan)
         for w in range(world):

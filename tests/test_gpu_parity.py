@@ -480,3 +480,8 @@ def test_errors_surface_as_python_exceptions():
     lab = FlatTree.from_newick(synth.kingman_newick(10, 1, states=2), 3, "mean", 2)
     with pytest.raises(ValueError):
         pk.kernel(lab, "(a:1,b:2);")          # different production-class schemes
+    sims = [synth.kingman_newick(12, i) for i in range(3)]
+    with pytest.raises(ValueError, match="math domain"):      # K = 0: math.log(0) at kamphir.py:300
+        PhyloKernel(decayFactor=0.0).score_batch(sims[0], sims)
+    with pytest.raises(ValueError, match="math domain"):
+        PhyloKernel(decayFactor=0.0).score_batch(sims[0], [FlatTree.from_newick(s) for s in sims])

@@ -116,3 +116,32 @@ def test_two_ranks_sharded_proposal_scores(tmp_path, n):
     mp.spawn(_score_worker, args=(2, _free_port(), n, str(tmp_path)), nprocs=2, join=True)
     ok = np.load(tmp_path / "ok.npy")
     assert ok.all(), ok
+
+
+def _failing_score_worker(rank, world, port, result_dir):
+    import torch.distributed as dist
+    from kamphir_b200.score import sharded_scores
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def score_fn(part):      # rank 1's share holds a replicate with K = 0 (math.log(0) at kamphir.py:300)
+        if rank == 1:
+            raise ValueError("math domain error (kamphir.py:300): K = 0 for replicate 0")
+        return dict(score=np.ones(len(part)), knorm=np.ones(len(part)), ref_denom=1.0)
+
+    raised = False
+    try:
+        sharded_scores(score_fn, ["t%d" % i for i in range(5)], rank, world)
+    except ValueError:
+        raised = True
+    np.save(os.path.join(result_dir, "raised%d.npy" % rank), np.array([raised]))
+    dist.barrier()           # reached by both ranks: nobody is left waiting in the all-gather
+    dist.destroy_process_group()
+
+
+def test_two_ranks_raise_together_when_one_share_fails(tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_failing_score_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert np.load(tmp_path / "raised0.npy").all() and np.load(tmp_path / "raised1.npy").all()
