@@ -142,7 +142,9 @@ int pk_forest_kernel_pairs(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb
 
 /* The ABC objective's inner loop, kamphir.py:288-306 + :434-450, for one target tree and nsims replicates:
  *   k[s] = K(obs, sim_s), denom[s] = K(sim_s, sim_s), khat[s] = exp(log k - (log ref_denom + log denom)/2).
- * *ref_denom = K(obs,obs) (kamphir.py:157) is computed when passed as NaN or <= 0 and returned. Any output may be NULL. */
+ * *ref_denom = K(obs,obs) (kamphir.py:157) is computed when passed as NaN or <= 0 and returned. Any output may be NULL.
+ * Where the reference's math.log(0) raises (K = 0: decayFactor 0, or labelled trees without a common production class)
+ * khat[s] is NaN or 0 and the call still succeeds; the Python mirror turns k <= 0 into the reference's ValueError. */
 int pk_score_batch(pk_ctx *ctx, const pk_tree *obs, const pk_tree *const *sims, int32_t nsims, const pk_params *params,
                    double *ref_denom, double *out_k, double *out_denom, double *out_khat);
 
