@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 64    ? (sizeof(T) == 4 ? 16 
         //      (child productions differ).  A cell (i, j) is only ever read by the cell of the two parents, and only when
         //      i and j have the same parent code; columns are ordered by (class, parent code), so row i stores just the
         //      contiguous column group with its own parent code: R cells per pair instead of M.
-        for (int c = tid; c < ncls; c += NT) s_cntB[c] = clsB[c + 1] - clsB[c];      // a one-warp CTA has fewer threads than 64 classes
+        if (tid < ncls) s_cntB[tid] = clsB[tid + 1] - clsB[tid];      // the host launches at least as many threads as classes
         if (tid == 0) {
             cells.st(0, tipf);       // tip x tip child factor (phyloK2.py:194-196)
             cells.st(1, (T)1);       // factor of a child slot whose productions differ (phyloK2.py:191-192)
@@ -1290,6 +1290,7 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
     }
     int nt = std::min(1024, std::max(64, (typ_w + 31) & ~31));
     if (ctx->cfg_threads) nt = ctx->cfg_threads;
+    if (nt < fa->ncls) nt = 64;      // the kernel fills its per-class tables with one thread per class (<= 64 classes)
 
     // C in shared memory only when that costs no resident CTAs: with C in a global slab the CTAs of small pairs stay
     // L2-resident anyway and more pairs per SM hide the level barriers better (measured: profiles/r01_summary.md)
