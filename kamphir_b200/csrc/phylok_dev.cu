@@ -19,7 +19,9 @@
 // The branch lengths are pre-scaled per pair so that the squared distance is the exponent of the Gaussian in binary
 // octaves (fp64: table + degree-4 polynomial + integer exponent add, 8 fp64 instructions; fp32: one MUFU.EX2).
 // Stored cells live in shared memory for tiny pairs, otherwise in a per-CTA slab in HBM that stays L1/L2-resident:
-// coalesced group writes, software-pipelined child-cell gathers.
+// coalesced group writes, software-pipelined child-cell gathers (fp32 and labelled trees: the pipeline also runs past the
+// end of a rectangle, PK_OVERRUN).  The kernel is instantiated per CTA-size tier (64 ... 1024 threads), each with the
+// register budget, resident CTAs per SM and rows in flight that measured best (table in DESIGN.md section 4).
 // No tensor cores (not a contraction), no CPU fallback.
 #include <cuda_runtime.h>
 
