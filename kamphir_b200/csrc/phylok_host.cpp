@@ -178,6 +178,17 @@ inline bool is_punct(char c) { return kCls.t[(unsigned char)c] == 1; }
 inline bool is_space(char c) { return kCls.t[(unsigned char)c] == 2; }
 inline bool is_token_end(char c) { return kCls.t[(unsigned char)c] != 0; }
 
+// eight ASCII digits at once (little-endian word, first character in the low byte)
+inline bool all_digits8(uint64_t w) {
+    return (((w & 0xF0F0F0F0F0F0F0F0ull) | (((w + 0x0606060606060606ull) & 0xF0F0F0F0F0F0F0F0ull) >> 4)) ==
+            0x3333333333333333ull);
+}
+inline uint32_t digits8(uint64_t w) {
+    w = (w & 0x0F0F0F0F0F0F0F0Full) * 2561 >> 8;                  // pairs: d0 * 10 + d1
+    w = (w & 0x00FF00FF00FF00FFull) * 6553601 >> 16;              // quads
+    return (uint32_t)((w & 0x0000FFFF0000FFFFull) * 42949672960001ull >> 32);
+}
+
 // Branch lengths: digits[.digits][e[+-]digits] with at most 19 significant digits and a power of ten within 10^22 is
 // the exact case of Clinger's fast path -- the decimal mantissa fits a double exactly (< 2^53) and so does the power
 // of ten, so one correctly rounded multiplication or division gives the correctly rounded result, the same double
@@ -319,8 +330,21 @@ int parse_one(const char *text, size_t b, size_t e, RawTree &t, bool ladderize, 
                 }
                 if (q < end && *q == '.') {
                     ++q;
+                    // eight fraction digits per step while they last (simulators write 10-12 of them): `digits` then
+                    // counts 8 for a block that starts the mantissa with zeros -- an upper bound, which at worst sends
+                    // a 12+-digit mantissa behind many zeros to parse_length (same value, slower)
+                    while (end - q >= 8) {
+                        uint64_t w;
+                        std::memcpy(&w, q, 8);
+                        if (!all_digits8(w)) break;
+                        const uint32_t v8 = digits8(w);
+                        if (m || v8) { digits += 8; if (digits <= 19) m = m * 100000000u + v8; }
+                        any = true;
+                        frac += 8;
+                        q += 8;
+                    }
                     while (q < end && (unsigned)(*q - '0') < 10u) {
-                        if (m || *q != '0') { ++digits; m = m * 10 + (unsigned)(*q - '0'); }
+                        if (m || *q != '0') { ++digits; if (digits <= 19) m = m * 10 + (unsigned)(*q - '0'); }
                         any = true;
                         ++frac;
                         ++q;

@@ -184,3 +184,32 @@ def test_worker_pool_survives_fork():
     assert all(x == [59] * 40 for x in out)
     again = FlatTree.many_from_newick("\n".join(nwk), nthreads=4)         # and the parent's pool still works
     assert [f.n_internal for f in again] == [59] * 64
+
+
+def test_branch_length_text_parses_like_float():
+    """The one-pass branch-length parser (8 digits per step, exact power-of-ten scaling, fallback for everything else)
+    returns the double Python's float() -- i.e. Bio.Phylo's Newick reader -- returns, on awkward digit counts too."""
+    import random
+    rnd = random.Random(5)
+    toks = []
+    while len(toks) < 3000:
+        k = rnd.choice([0, 1, 2, 3, 5, 7, 8, 9, 10, 11, 12, 15, 16, 17, 18, 19, 20, 24])
+        ip = rnd.choice(['0', '7', '12', '123456789', '0000', '', '00012'])
+        fr = ''.join(rnd.choice('0123456789') for _ in range(k))
+        if rnd.random() < 0.3:
+            fr = '0' * rnd.randint(1, 12) + fr
+        ex = rnd.choice(['', 'e-05', 'E+3', 'e10', 'e-300', 'e0'])
+        if not ip and not fr:
+            continue
+        tok = (ip + '.' + fr if fr or rnd.random() < 0.5 else (ip or '1')) + ex
+        try:
+            float(tok)
+        except ValueError:
+            continue
+        if tok[0] in '.eE' and (len(tok) == 1 or tok[1] in 'eE'):
+            continue
+        toks.append(tok)
+    for a, b in zip(toks[0::2], toks[1::2]):
+        ft = FlatTree.from_newick("(x:%s,y:%s);" % (a, b), 0, "none")
+        got = np.asarray(ft.export()[-1]).ravel()
+        assert got[0] == float(a) and got[1] == float(b), (a, b, got)
