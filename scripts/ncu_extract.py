@@ -1,5 +1,5 @@
 """Turns one `ncu --set full` capture of the DP kernel into the two files under profiles/ that bench.py and the summary
-cite:  python scripts/ncu_extract.py gpurun_out/prof.ncu-rep <dps in the captured launch> <label>
+cite:  python scripts/ncu_extract.py gpurun_out/prof.ncu-rep <dps in the captured launch> <label> [file suffix]
 (developer tool; needs the `ncu` CLI, no GPU)."""
 import csv
 import io
@@ -26,6 +26,8 @@ KEEP = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 def main():
     rep, dps, label = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+    suffix = sys.argv[4] if len(sys.argv) > 4 else ""          # e.g. "_fp32": a second capture next to the fp64 one
+    prec = 32 if "32" in suffix else 64
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, vals = rows[0], rows[1], rows[2]
@@ -35,7 +37,7 @@ def main():
         if any(h == k or (k.endswith("_") and h.startswith(k) and "not_issued" not in h.lower()) for k in KEEP):
             out.append((h, u, v))
             got[h] = (u, v)
-    with open("profiles/r01_dp_kernel_ncu_full_selected.csv", "w", newline="") as f:
+    with open("profiles/r01_dp_kernel%s_ncu_full_selected.csv" % suffix, "w", newline="") as f:
         csv.writer(f).writerows(out)
 
     def to_bytes(name):
@@ -46,9 +48,9 @@ def main():
     u, v = got["gpu__time_duration.sum"]
     ms = float(v) * {"ms": 1, "us": 1e-3, "s": 1e3}[u]
     json.dump({"command": label, "dps_in_launch": dps, "dram_bytes_read": rd, "dram_bytes_write": wr,
-               "kernel_ms_under_ncu": ms, "n_tips": 500, "precision": 64, "dram_bytes_per_dp": (rd + wr) / dps},
-              open("profiles/r01_dram_traffic.json", "w"), indent=1)
-    print("wrote profiles/r01_dp_kernel_ncu_full_selected.csv (%d metrics) and profiles/r01_dram_traffic.json" % (len(out) - 1))
+               "kernel_ms_under_ncu": ms, "n_tips": 500, "precision": prec, "dram_bytes_per_dp": (rd + wr) / dps},
+              open("profiles/r01_dram_traffic%s.json" % suffix, "w"), indent=1)
+    print("wrote profiles/r01_dp_kernel%s_ncu_full_selected.csv (%d metrics) and profiles/r01_dram_traffic%s.json" % (suffix, len(out) - 1, suffix))
 
 
 if __name__ == "__main__":
