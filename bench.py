@@ -344,11 +344,13 @@ def run_ours(args):
         # DRAM traffic of the same kernel from the committed ncu --set full capture, scaled per DP to this launch
         traffic, traffic_src = None, None
         try:
-            cap = json.load(open(os.path.join(REPO, "profiles", "r01_dram_traffic.json")))
+            cap_name = "r01_dram_traffic%s.json" % ("_fp32" if args.precision == 32 else "")
+            cap = json.load(open(os.path.join(REPO, "profiles", cap_name)))
             if cap.get("n_tips") == args.tips and cap.get("precision") == args.precision:
                 traffic = cap["dram_bytes_per_dp"] * stats["dps"]
-                traffic_src = ("profiles/r01_dram_traffic.json: (dram__bytes_read.sum + dram__bytes_write.sum) / %d DPs "
-                               "of one captured Gram launch x %d DPs of this launch" % (cap["dps_in_launch"], stats["dps"]))
+                traffic_src = ("profiles/%s: (dram__bytes_read.sum + dram__bytes_write.sum) / %d DPs "
+                               "of one captured Gram launch x %d DPs of this launch"
+                               % (cap_name, cap["dps_in_launch"], stats["dps"]))
         except (OSError, ValueError, KeyError):
             pass
         node_pairs_total = None
