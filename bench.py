@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32])
     ap.add_argument("--tile", type=int, default=32)
     ap.add_argument("--gather", default="p2p", choices=["p2p", "allreduce"])
-    ap.add_argument("--cpu-sample", type=int, default=256, help="DPs in the single-process cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=512, help="DPs in the single-process cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-sample", type=int, default=64)
     return ap.parse_args()
