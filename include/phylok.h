@@ -75,8 +75,9 @@ int pk_device_count(void);                       /* CUDA devices visible, 0 when
  * pk_tree_from_newick : Phylo.read (kamphir.py:323) + prep (kamphir.py:279-282) + annotate (phyloK2.py:132-146)
  * pk_trees_from_newick: Phylo.parse over a multi-tree handle (kamphir.py:112, phyloK2.py:74); returns an array
  *                       allocated by the library (free each tree, then pk_tree_array_free).
- * n_states > 0 turns on tip-state productions: state = integer after the last '_' of the tip name
- *                       (rcolgem.py:274,376,588); extension with no reference implementation.
+ * n_states = S > 0 turns on tip-state productions: state = integer after the last '_' of the tip name, 0 .. S-1 or
+ *                       rcolgem's 1 .. S (rcolgem.py:274,376,588; S counts as 0); extension with no reference
+ *                       implementation.
  * nthreads: worker threads for the multi-tree form (<= 0: hardware concurrency). */
 int pk_tree_from_newick(const char *text, size_t len, int prep_flags, int normalize, int n_states, pk_tree **out);
 int pk_trees_from_newick(const char *text, size_t len, int prep_flags, int normalize, int n_states, int nthreads,
@@ -93,6 +94,9 @@ void pk_tree_array_free(pk_tree **arr);
 int pk_tree_from_arrays(int32_t n_internal, const int32_t *cidx, const double *bl, const uint8_t *cls,
                         int32_t n_classes, pk_tree **out);
 void pk_tree_free(pk_tree *t);
+/* node heights (any order), un-normalised tree height and normalisation divisor of a tree built with pk_tree_from_arrays
+ * (what kcoal, kamphir.py:255-269, needs and the arrays do not carry); the Python mirror uses it to rebuild pickled trees */
+int pk_tree_set_heights(pk_tree *t, const double *heights, int32_t n, double height, double scale);
 int pk_tree_get_info(const pk_tree *t, pk_tree_info *info);
 /* post-order arrays as annotate_tree defines them (for parity tests): prod[n], cprod[2n], cidx[2n], bl[2n] */
 int pk_tree_export(const pk_tree *t, uint8_t *prod, uint8_t *cprod, int32_t *cidx, double *bl);
@@ -100,7 +104,9 @@ int pk_tree_export(const pk_tree *t, uint8_t *prod, uint8_t *cprod, int32_t *cid
 int pk_tree_node_heights(const pk_tree *t, double *heights /* n_internal */);
 /* exact work of one DP: counts = {node pairs, matched cells M, child-cell reads R} */
 int pk_pair_counts(const pk_tree *a, const pk_tree *b, int64_t counts[3]);
-/* kcoal of kamphir.py:260-269: cosine of the two ascending node-height vectors (sim indexed into target) */
+/* kcoal of kamphir.py:260-269: cosine of the two ascending node-height vectors (sim indexed into target).
+ * PK_ERR_INVALID where the reference raises: more internal nodes than the target (IndexError, :264), zero norm
+ * (ZeroDivisionError, :269). */
 int pk_kcoal(const pk_tree *sim, const pk_tree *target, double *out);
 /* the same for every replicate of one proposal (kamphir.py:434-450 loops over them): out[s] = kcoal(sims[s], target) */
 int pk_kcoal_batch(const pk_tree *const *sims, int32_t nsims, const pk_tree *target, double *out);
@@ -117,6 +123,12 @@ int pk_ctx_configure(pk_ctx *ctx, int32_t threads, int32_t ctas_per_sm, int32_t 
  * ctx stream; blocks until it finished), launches = DP kernels launched since ctx creation, path = 0 (C in shared
  * memory) / 1 (C in HBM slabs), launch_cfg = {grid, threads per CTA, dynamic shared memory bytes}. Any may be NULL. */
 int pk_ctx_last_stats(pk_ctx *ctx, double *ms, int64_t *launches, int32_t *path, int32_t launch_cfg[3]);
+
+/* Results that came out non-finite since the last reset, counted by the DP kernel itself.  In fp32 mode a cell beyond
+ * 3e38 overflows (decay factors above ~0.25 on deep, similar trees); the host-resident entry points (pk_kernel_pairs,
+ * pk_score_batch, pk_score_newick_batch, pk_gram) re-evaluate such pairs in fp64 themselves, callers of the
+ * device-resident forms check this counter (GramRunner.fetch raises).  Blocks until the stream is idle. */
+int pk_ctx_nonfinite(pk_ctx *ctx, int64_t *count, int reset);
 
 int pk_forest_upload(pk_ctx *ctx, const pk_tree *const *trees, int32_t n, int32_t precision, pk_forest **out);
 /* Multi-GPU replication of a forest without packing it W times: every rank lays the whole forest out (same offsets,
@@ -140,6 +152,11 @@ int pk_kernel_pairs(pk_ctx *ctx, const pk_tree *const *A, int32_t nA, const pk_t
 int pk_forest_kernel_pairs(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, const int32_t *d_pairs,
                            int32_t npairs, const pk_params *params, double *d_out_k);
 
+/* Device-resident forests, HOST pair list and HOST results: one launch, one synchronisation (what PhyloKernel.kernel
+ * uses for trees whose single-tree forests it keeps on the device between calls). */
+int pk_forest_kernel_pairs_host(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, const int32_t *pairs,
+                                int32_t npairs, const pk_params *params, double *out_k);
+
 /* The ABC objective's inner loop, kamphir.py:288-306 + :434-450, for one target tree and nsims replicates:
  *   k[s] = K(obs, sim_s), denom[s] = K(sim_s, sim_s), khat[s] = exp(log k - (log ref_denom + log denom)/2).
  * *ref_denom = K(obs,obs) (kamphir.py:157) is computed when passed as NaN or <= 0 and returned. Any output may be NULL.
@@ -157,11 +174,16 @@ int pk_score_newick_batch(pk_ctx *ctx, const pk_tree *obs, const char *const *si
                           double *ref_denom, double kadj, double *out_k, double *out_denom, double *out_khat,
                           double *out_kcoal, double *out_score, double *out_mean);
 
+/* FORWARD NOTE on the tile partition: pk_gram_part_pairs / pk_gram_part_tiles below describe the uniform partition (tile t
+ * to part t % nparts); a forest-aware call (pk_forest_gram_part, pk_forest_gram_stats, pk_forest_gram_part_tiles) deals the
+ * tiles by cost = node pairs of the tile, which for equal-sized trees differs only in where the half-filled
+ * diagonal tiles go.  Either way the parts are disjoint and cover the upper triangle. */
+
 /* All-pairs Gram matrix, the working form of PhyloKernel.compute_matrix (phyloK2.py:148-156): out is N x N row-major,
  * symmetric; normalised = 0: raw K (reference semantics); 1: K / sqrt(K_ii K_jj).  Host-resident form. */
 int pk_gram(pk_ctx *ctx, const pk_tree *const *trees, int32_t n, const pk_params *params, int normalised, double *out);
-/* Device-resident, shardable form.  The upper triangle is cut into tile x tile blocks, block t belongs to part
- * t % nparts; this call computes the blocks of `part` and writes both (i,j) and (j,i) into d_out (N x N, leading
+/* Device-resident, shardable form.  The upper triangle is cut into tile x tile blocks, dealt to the parts by cost
+ * (see the note above); this call computes the blocks of `part` and writes both (i,j) and (j,i) into d_out (N x N, leading
  * dimension ld, DEVICE pointer -- may be a peer/IPC mapping of another GPU's buffer so results cross NVLink once,
  * written by the DP kernel itself).  d_diag (N doubles, device) receives K_ii; it is computed by every part.
  * Asynchronous on the ctx stream. */
@@ -171,6 +193,9 @@ int pk_forest_gram_part(pk_ctx *ctx, const pk_forest *f, const pk_params *params
 int pk_gram_part_pairs(int32_t n, int32_t tile, int32_t part, int32_t nparts, int64_t *npairs);
 /* the (row-block, column-block) coordinates of that part's tiles; pass tiles = NULL to query the count (host only) */
 int pk_gram_part_tiles(int32_t n, int32_t tile, int32_t part, int32_t nparts, int32_t *tiles, int64_t *ntiles);
+
+/* the tiles pk_forest_gram_part(part, nparts) evaluates for THIS forest (cost-weighted deal); tiles = NULL queries the count */
+int pk_forest_gram_part_tiles(const pk_forest *f, int32_t tile, int32_t part, int32_t nparts, int32_t *tiles, int64_t *ntiles);
 
 /* cross-process sharing of a device buffer (one result matrix on rank 0, written by all ranks over NVLink) */
 /* page-locked host buffers for results fetched every step (GramRunner.fetch) */

@@ -39,6 +39,7 @@ SIGNATURES = {
     "pk_tree_array_free": (None, [_PP]),
     "pk_tree_from_arrays": (ctypes.c_int, [_I32, _P, _P, _P, _I32, _PP]),
     "pk_tree_free": (None, [_P]),
+    "pk_tree_set_heights": (ctypes.c_int, [_P, _P, _I32, _D, _D]),
     "pk_tree_get_info": (ctypes.c_int, [_P, ctypes.POINTER(pk_tree_info)]),
     "pk_tree_export": (ctypes.c_int, [_P, _P, _P, _P, _P]),
     "pk_tree_node_heights": (ctypes.c_int, [_P, _P]),
@@ -51,6 +52,7 @@ SIGNATURES = {
     "pk_ctx_sync": (ctypes.c_int, [_P]),
     "pk_ctx_configure": (ctypes.c_int, [_P, _I32, _I32, _I32]),
     "pk_ctx_last_stats": (ctypes.c_int, [_P, ctypes.POINTER(_D), ctypes.POINTER(_I64), ctypes.POINTER(_I32), _P]),
+    "pk_ctx_nonfinite": (ctypes.c_int, [_P, ctypes.POINTER(_I64), ctypes.c_int]),
     "pk_forest_upload": (ctypes.c_int, [_P, _P, _I32, _I32, _PP]),
     "pk_forest_upload_part": (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _I32, _PP]),
     "pk_forest_device_range": (ctypes.c_int, [_P, _I32, _I32, _PP, ctypes.POINTER(_I64)]),
@@ -60,6 +62,7 @@ SIGNATURES = {
     "pk_forest_gram_stats": (ctypes.c_int, [_P, _I32, _I32, _I32, _P]),
     "pk_kernel_pairs": (ctypes.c_int, [_P, _P, _I32, _P, _I32, _P, _I32, ctypes.POINTER(pk_params), _P]),
     "pk_forest_kernel_pairs": (ctypes.c_int, [_P, _P, _P, _P, _I32, ctypes.POINTER(pk_params), _P]),
+    "pk_forest_kernel_pairs_host": (ctypes.c_int, [_P, _P, _P, _P, _I32, ctypes.POINTER(pk_params), _P]),
     "pk_score_newick_batch": (ctypes.c_int, [_P, _P, _P, _P, _I32, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                              ctypes.POINTER(pk_params), ctypes.POINTER(_D), _D, _P, _P, _P, _P, _P,
                                              ctypes.POINTER(_D)]),
@@ -68,6 +71,7 @@ SIGNATURES = {
     "pk_forest_gram_part": (ctypes.c_int, [_P, _P, ctypes.POINTER(pk_params), ctypes.c_int, _I32, _I32, _I32, _P, _I64, _P]),
     "pk_gram_part_pairs": (ctypes.c_int, [_I32, _I32, _I32, _I32, ctypes.POINTER(_I64)]),
     "pk_gram_part_tiles": (ctypes.c_int, [_I32, _I32, _I32, _I32, _P, ctypes.POINTER(_I64)]),
+    "pk_forest_gram_part_tiles": (ctypes.c_int, [_P, _I32, _I32, _I32, _P, ctypes.POINTER(_I64)]),
     "pk_host_alloc": (ctypes.c_int, [_P, _SZ, _PP]),
     "pk_host_free": (ctypes.c_int, [_P, _P]),
     "pk_device_alloc": (ctypes.c_int, [_P, _SZ, _PP]),

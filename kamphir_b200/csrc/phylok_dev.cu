@@ -70,6 +70,7 @@ struct DpArgs {
     void *scratch;                  // HBM path: per-CTA C slabs
     long long slab_elems;
     unsigned long long *counter;    // work counter
+    unsigned long long *nonfinite;  // per-context count of results that came out inf / NaN (fp32 cells overflow beyond 3e38)
     int tree_region;                // shared-memory bytes reserved for the staged ROW part
     int col_region;                 // ... and for the staged COLUMN part
     int rowinfo_bytes;              // row offsets
@@ -674,6 +675,9 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 64    ? (sizeof(T) == 4 ? 16 
         if (tid == 0) {
             double k = 0.0;
             for (int i = 0; i < NW; ++i) k += s_part[i];
+            // every cell is a term of K, so a cell that overflowed (fp32 mode: beyond 3e38, which large decay factors reach
+            // on deep similar trees) or an inf * 0 shows up here; the host entry points re-evaluate such pairs in fp64
+            if (!(fabs(k) <= 1.7976931348623157e308)) atomicAdd(a.nonfinite, 1ull);
             if (a.mode == 0) {
                 a.out[w] = k;
             } else if (a.mode == 1) {
@@ -762,10 +766,29 @@ struct pk_forest {
 
 static const int kCounterRing = 64;
 
-static int ensure_device(pk_ctx *ctx) {
-    PK_CUDA(cudaSetDevice(ctx->device));
-    return PK_OK;
-}
+// Every entry point runs on its context's device and leaves the calling thread's current device as it found it (a
+// torch caller with several GPUs does not expect a library call to switch devices under it).
+struct DeviceGuard {
+    int prev = -1, want;
+    cudaError_t err;
+    explicit DeviceGuard(int dev) : want(dev) {
+        err = cudaGetDevice(&prev);
+        if (err != cudaSuccess) {
+            prev = -1;
+            cudaGetLastError();
+        }
+        err = prev == dev ? cudaSuccess : cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != want) cudaSetDevice(prev);
+    }
+};
+#define PK_ENTER(ctx)                                                                                       \
+    DeviceGuard guard__((ctx)->device);                                                                     \
+    if (guard__.err != cudaSuccess)                                                                         \
+        return pk_fail(PK_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(guard__.err));      \
+    int rc = PK_OK;                                                                                         \
+    (void)rc
 
 extern "C" int pk_device_count(void) {
     int n = 0;
@@ -790,16 +813,29 @@ extern "C" int pk_ctx_create(int device, pk_ctx **out) {
     if (device < 0 || device >= n) return pk_fail(PK_ERR_INVALID, "device index out of range");
     cudaDeviceProp prop;
     PK_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10)
+    // the library carries one sm_100a cubin and no PTX: any other architecture (sm_103, sm_12x, ...) has no kernel image
+    if (prop.major != 10 || prop.minor != 0)
         return pk_fail(PK_ERR_NODEVICE, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
                                             std::to_string(prop.minor) + "; this library is built for sm_100a only");
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess)
+        return pk_fail(PK_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(guard.err));
+    {
+        cudaFuncAttributes fa;      // proves that the kernel image loads on this device before anything is allocated
+        cudaError_t pe = cudaFuncGetAttributes(&fa, pk_zero_kernel);
+        if (pe != cudaSuccess) {
+            cudaGetLastError();
+            return pk_fail(PK_ERR_NODEVICE, std::string("no kernel image for device '") + prop.name + "': " + cudaGetErrorString(pe));
+        }
+    }
     pk_ctx *ctx = new pk_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
-    cudaError_t err = cudaSetDevice(device);
+    cudaError_t err = cudaSuccess;
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-    if (err == cudaSuccess) err = cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * kCounterRing);
+    if (err == cudaSuccess) err = cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * (kCounterRing + 1));
+    if (err == cudaSuccess) err = cudaMemset(ctx->d_counters, 0, sizeof(unsigned long long) * (kCounterRing + 1));
     if (err == cudaSuccess) err = cudaEventCreate(&ctx->ev[0]);
     if (err == cudaSuccess) err = cudaEventCreate(&ctx->ev[1]);
     if (err == cudaSuccess) err = cudaEventCreateWithFlags(&ctx->pinned_ev, cudaEventDisableTiming);
@@ -813,7 +849,7 @@ extern "C" int pk_ctx_create(int device, pk_ctx **out) {
 
 extern "C" void pk_ctx_destroy(pk_ctx *ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
@@ -829,8 +865,7 @@ extern "C" void pk_ctx_destroy(pk_ctx *ctx) {
 
 extern "C" int pk_ctx_set_stream(pk_ctx *ctx, void *cuda_stream) {
     if (!ctx) return pk_fail(PK_ERR_INVALID, "null ctx");
-    int rc = ensure_device(ctx);
-    if (rc) return rc;
+    PK_ENTER(ctx);
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (cuda_stream) {
@@ -845,8 +880,7 @@ extern "C" int pk_ctx_set_stream(pk_ctx *ctx, void *cuda_stream) {
 
 extern "C" int pk_ctx_sync(pk_ctx *ctx) {
     if (!ctx) return pk_fail(PK_ERR_INVALID, "null ctx");
-    int rc = ensure_device(ctx);
-    if (rc) return rc;
+    PK_ENTER(ctx);
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
     return PK_OK;
 }
@@ -863,8 +897,7 @@ extern "C" int pk_ctx_configure(pk_ctx *ctx, int32_t threads, int32_t ctas_per_s
 
 extern "C" int pk_ctx_last_stats(pk_ctx *ctx, double *ms, int64_t *launches, int32_t *path, int32_t launch_cfg[3]) {
     if (!ctx) return pk_fail(PK_ERR_INVALID, "null ctx");
-    int rc = ensure_device(ctx);
-    if (rc) return rc;
+    PK_ENTER(ctx);
     if (ms) {
         *ms = 0.0;
         if (ctx->ev_valid) {
@@ -881,6 +914,17 @@ extern "C" int pk_ctx_last_stats(pk_ctx *ctx, double *ms, int64_t *launches, int
         launch_cfg[1] = ctx->last_threads;
         launch_cfg[2] = ctx->last_smem;
     }
+    return PK_OK;
+}
+
+extern "C" int pk_ctx_nonfinite(pk_ctx *ctx, int64_t *count, int reset) {
+    if (!ctx || !count) return pk_fail(PK_ERR_INVALID, "null argument");
+    PK_ENTER(ctx);
+    unsigned long long v = 0;
+    PK_CUDA(cudaMemcpyAsync(&v, ctx->d_counters + kCounterRing, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+    if (reset) PK_CUDA(cudaMemsetAsync(ctx->d_counters + kCounterRing, 0, sizeof(v), ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    *count = (int64_t)v;
     return PK_OK;
 }
 
@@ -964,8 +1008,7 @@ static int forest_upload_impl(pk_ctx *ctx, const pk_tree *const *trees, int32_t 
     if (part_lo < 0 || part_hi > n || part_lo > part_hi) return pk_fail(PK_ERR_INVALID, "tree range out of bounds");
     if (precision != 64 && precision != 32) return pk_fail(PK_ERR_INVALID, "precision must be 64 or 32");
     *out = nullptr;
-    int rc = ensure_device(ctx);
-    if (rc) return rc;
+    PK_ENTER(ctx);
     const int ncls = trees[0] ? trees[0]->ncls : 0;
     size_t total = 0;
     for (int32_t i = 0; i < n; ++i) {
@@ -1096,7 +1139,7 @@ extern "C" int pk_forest_device_range(const pk_forest *f, int32_t tree_lo, int32
 
 extern "C" void pk_forest_free(pk_forest *f) {
     if (!f) return;
-    cudaSetDevice(f->ctx->device);
+    DeviceGuard guard(f->ctx->device);
     if (f->d_blocks) pool_release(f->ctx, f->d_blocks, f->alloc_bytes);
     delete f;
 }
@@ -1332,6 +1375,7 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
     args.counter = ctx->d_counters + (ctx->counter_next++ % kCounterRing);
     PK_CUDA(cudaMemsetAsync(args.counter, 0, sizeof(unsigned long long), ctx->stream));
 #endif
+    args.nonfinite = ctx->d_counters + kCounterRing;
     PK_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     e = PK_DISPATCH(launch_t, ctx, args, grid, nt, smem, ctx->stream);
     if (e != cudaSuccess) return pk_fail(PK_ERR_CUDA, std::string("DP kernel launch: ") + cudaGetErrorString(e));
@@ -1357,8 +1401,7 @@ extern "C" int pk_forest_kernel_pairs(pk_ctx *ctx, const pk_forest *fa, const pk
                                       int32_t npairs, const pk_params *params, double *d_out_k) {
     if (!ctx || !fa || !fb || !params || (npairs > 0 && (!d_pairs || !d_out_k)))
         return pk_fail(PK_ERR_INVALID, "null argument");
-    int rc = ensure_device(ctx);
-    if (rc) return rc;
+    PK_ENTER(ctx);
     DpArgs args;
     std::memset(&args, 0, sizeof(args));
     args.mode = 0;
@@ -1366,6 +1409,36 @@ extern "C" int pk_forest_kernel_pairs(pk_ctx *ctx, const pk_forest *fa, const pk
     args.total = npairs;
     args.out = d_out_k;
     return launch_dp(ctx, fa, fb, args, params);
+}
+
+extern "C" int pk_forest_kernel_pairs_host(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, const int32_t *pairs,
+                                           int32_t npairs, const pk_params *params, double *out_k) {
+    if (!ctx || !fa || !fb || !params || (npairs > 0 && (!pairs || !out_k))) return pk_fail(PK_ERR_INVALID, "null argument");
+    if (npairs <= 0) return PK_OK;
+    for (int32_t p = 0; p < npairs; ++p)
+        if (pairs[2 * p] < 0 || pairs[2 * p] >= fa->n || pairs[2 * p + 1] < 0 || pairs[2 * p + 1] >= fb->n)
+            return pk_fail(PK_ERR_INVALID, "pair index out of range");
+    PK_ENTER(ctx);
+    const size_t pb = sizeof(int32_t) * 2 * (size_t)npairs, ob = sizeof(double) * (size_t)npairs;
+    const size_t pb_al = (pb + 255) & ~(size_t)255;
+    rc = ensure_tmp(ctx, pb_al + ob);
+    if (rc == PK_OK) rc = ensure_pinned(ctx, pb_al + ob);
+    if (rc) return rc;
+    unsigned char *d = static_cast<unsigned char *>(ctx->d_tmp);
+    unsigned char *h = static_cast<unsigned char *>(ctx->h_pinned);
+    std::memcpy(h, pairs, pb);
+    PK_CUDA(cudaMemcpyAsync(d, h, pb, cudaMemcpyHostToDevice, ctx->stream));
+    rc = pk_forest_kernel_pairs(ctx, fa, fb, reinterpret_cast<int32_t *>(d), npairs, params, reinterpret_cast<double *>(d + pb_al));
+    if (rc) {
+        std::string keep(pk_last_error());
+        cudaStreamSynchronize(ctx->stream);
+        pk_set_error(keep);
+        return rc;
+    }
+    PK_CUDA(cudaMemcpyAsync(h + pb_al, d + pb_al, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    PK_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(out_k, h + pb_al, ob);
+    return PK_OK;
 }
 
 // `while_running`, if set, is called after the launch is queued and before the host waits for the results: host work
@@ -1378,8 +1451,7 @@ static int kernel_pairs_impl(pk_ctx *ctx, const pk_tree *const *A, int32_t nA, c
     for (int32_t p = 0; p < npairs; ++p)
         if (pairs[2 * p] < 0 || pairs[2 * p] >= nA || pairs[2 * p + 1] < 0 || pairs[2 * p + 1] >= nB)
             return pk_fail(PK_ERR_INVALID, "pair index out of range");
-    int rc = ensure_device(ctx);
-    if (rc) return rc;
+    PK_ENTER(ctx);
     const int prec = params->precision == 32 ? 32 : 64;
     pk_forest *fa = nullptr, *fb = nullptr;
     static const bool trace = std::getenv("PK_TRACE") != nullptr;
@@ -1430,6 +1502,27 @@ static int kernel_pairs_impl(pk_ctx *ctx, const pk_tree *const *A, int32_t nA, c
     if (fb && fb != fa) pk_forest_free(fb);
     pk_forest_free(fa);
     if (rc) pk_set_error(keep);
+    if (rc == PK_OK && prec == 32) {
+        // fp32 cells overflow beyond 3e38 (decay factors above ~0.25 on deep similar trees, e.g. the reference's own unit-test
+        // setting 0.5 on a caterpillar against itself): such a K arrives as inf / NaN and is evaluated again in fp64, which
+        // has the reference's range -- no inf or NaN of the fp32 mode reaches the caller
+        std::vector<int32_t> redo;
+        std::vector<int32_t> where;
+        for (int32_t p = 0; p < npairs; ++p)
+            if (!std::isfinite(out_k[p])) {
+                where.push_back(p);
+                redo.push_back(pairs[2 * p]);
+                redo.push_back(pairs[2 * p + 1]);
+            }
+        if (!where.empty()) {
+            pk_params p64 = *params;
+            p64.precision = 64;
+            std::vector<double> k64(where.size());
+            rc = kernel_pairs_impl(ctx, A, nA, B, nB, redo.data(), (int32_t)where.size(), &p64, k64.data(), nullptr);
+            if (rc == PK_OK)
+                for (size_t q = 0; q < where.size(); ++q) out_k[where[q]] = k64[q];
+        }
+    }
     return rc;
 }
 
@@ -1548,19 +1641,64 @@ extern "C" int pk_score_newick_batch(pk_ctx *ctx, const pk_tree *obs, const char
 // ---------------------------------------------------------------------------------------------------
 // Gram matrix
 // ---------------------------------------------------------------------------------------------------
-static int gram_tiles(int32_t n, int32_t tile, int32_t part, int32_t nparts, std::vector<int2> *tiles, int64_t *npairs) {
+// Tiles of the upper triangle that `part` of `nparts` evaluates.  Without a forest: tile t (row-major over tj >= ti)
+// belongs to part t % nparts.  With a forest: tiles are dealt by cost, cost(ti, tj) = sum over the tile's
+// DPs of n_i * n_j (the node pairs, to which M and the DP time are proportional): longest-processing-time greedy --
+// tiles by decreasing cost (ties in t order), each to the least loaded part (ties to the lowest part) -- then every part's
+// list back in t order.  Every rank computes the same assignment from the same host-side statistics.  For a forest of
+// equal-sized trees this deals the full tiles round-robin and then spreads the half-filled diagonal tiles evenly.
+static int gram_tiles(int32_t n, int32_t tile, int32_t part, int32_t nparts, std::vector<int2> *tiles, int64_t *npairs,
+                      const pk_forest *f = nullptr) {
     if (n < 1 || tile < 1 || (tile & (tile - 1)) || nparts < 1 || part < 0 || part >= nparts)
         return pk_fail(PK_ERR_INVALID, "gram: tile must be a power of two, 0 <= part < nparts");
     const int32_t nt = (n + tile - 1) / tile;
-    int64_t t = 0, cnt = 0;
+    auto tile_pairs = [&](int32_t ti, int32_t tj) {
+        const int64_t hi = std::min<int64_t>(n, (int64_t)(ti + 1) * tile) - (int64_t)ti * tile;
+        const int64_t wj = std::min<int64_t>(n, (int64_t)(tj + 1) * tile) - (int64_t)tj * tile;
+        return (ti == tj) ? hi * (hi + 1) / 2 : hi * wj;
+    };
+    int64_t cnt = 0;
+    if (!f || nparts == 1) {
+        int64_t t = 0;
+        for (int32_t ti = 0; ti < nt; ++ti)
+            for (int32_t tj = ti; tj < nt; ++tj, ++t) {
+                if (t % nparts != part) continue;
+                if (tiles) tiles->push_back(make_int2(ti, tj));
+                cnt += tile_pairs(ti, tj);
+            }
+        if (npairs) *npairs = cnt;
+        return PK_OK;
+    }
+    std::vector<double> s1(nt, 0.0), s2(nt, 0.0);      // per block of trees: sum n, sum n^2
+    for (int32_t i = 0; i < n; ++i) {
+        s1[i / tile] += (double)f->nint[i];
+        s2[i / tile] += (double)f->nint[i] * (double)f->nint[i];
+    }
+    struct Item { double cost; int64_t t; int32_t ti, tj; };
+    std::vector<Item> items;
+    items.reserve((size_t)nt * (nt + 1) / 2);
+    int64_t t = 0;
     for (int32_t ti = 0; ti < nt; ++ti)
-        for (int32_t tj = ti; tj < nt; ++tj, ++t) {
-            if (t % nparts != part) continue;
-            if (tiles) tiles->push_back(make_int2(ti, tj));
-            const int64_t hi = std::min<int64_t>(n, (int64_t)(ti + 1) * tile) - (int64_t)ti * tile;
-            const int64_t wj = std::min<int64_t>(n, (int64_t)(tj + 1) * tile) - (int64_t)tj * tile;
-            cnt += (ti == tj) ? hi * (hi + 1) / 2 : hi * wj;
-        }
+        for (int32_t tj = ti; tj < nt; ++tj, ++t)
+            items.push_back(Item{ti == tj ? 0.5 * (s1[ti] * s1[ti] + s2[ti]) : s1[ti] * s1[tj], t, ti, tj});
+    std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return a.cost > b.cost; });
+    // least loaded part first; (load, part) pairs in a small binary heap
+    std::vector<std::pair<double, int32_t>> heap;
+    for (int32_t p = 0; p < nparts; ++p) heap.emplace_back(0.0, p);
+    auto worse = [](const std::pair<double, int32_t> &a, const std::pair<double, int32_t> &b) { return a > b; };
+    std::make_heap(heap.begin(), heap.end(), worse);
+    std::vector<Item> mine;
+    for (const Item &it : items) {
+        std::pop_heap(heap.begin(), heap.end(), worse);
+        if (heap.back().second == part) mine.push_back(it);
+        heap.back().first += it.cost;
+        std::push_heap(heap.begin(), heap.end(), worse);
+    }
+    std::sort(mine.begin(), mine.end(), [](const Item &a, const Item &b) { return a.t < b.t; });
+    for (const Item &it : mine) {
+        if (tiles) tiles->push_back(make_int2(it.ti, it.tj));
+        cnt += tile_pairs(it.ti, it.tj);
+    }
     if (npairs) *npairs = cnt;
     return PK_OK;
 }
@@ -1586,10 +1724,27 @@ extern "C" int pk_gram_part_tiles(int32_t n, int32_t tile, int32_t part, int32_t
     return PK_OK;
 }
 
+extern "C" int pk_forest_gram_part_tiles(const pk_forest *f, int32_t tile, int32_t part, int32_t nparts, int32_t *tiles,
+                                         int64_t *ntiles) {
+    if (!f || !ntiles) return pk_fail(PK_ERR_INVALID, "null argument");
+    std::vector<int2> t;
+    int rc = gram_tiles(f->n, tile, part, nparts, &t, nullptr, f);
+    if (rc) return rc;
+    if (tiles) {
+        if (*ntiles < (int64_t)t.size()) return pk_fail(PK_ERR_INVALID, "tile buffer too small");
+        for (size_t k = 0; k < t.size(); ++k) {
+            tiles[2 * k] = t[k].x;
+            tiles[2 * k + 1] = t[k].y;
+        }
+    }
+    *ntiles = (int64_t)t.size();
+    return PK_OK;
+}
+
 extern "C" int pk_forest_gram_stats(const pk_forest *f, int32_t tile, int32_t part, int32_t nparts, int64_t counts[4]) {
     if (!f || !counts) return pk_fail(PK_ERR_INVALID, "null argument");
     std::vector<int2> tiles;
-    int rc = gram_tiles(f->n, tile, part, nparts, &tiles, nullptr);
+    int rc = gram_tiles(f->n, tile, part, nparts, &tiles, nullptr, f);
     if (rc) return rc;
     counts[0] = counts[1] = counts[2] = counts[3] = 0;
     for (const int2 &t : tiles)
@@ -1602,10 +1757,9 @@ extern "C" int pk_forest_gram_part(pk_ctx *ctx, const pk_forest *f, const pk_par
                                    int32_t part, int32_t nparts, double *d_out, int64_t ld, double *d_diag) {
     if (!ctx || !f || !params || !d_out) return pk_fail(PK_ERR_INVALID, "null argument");
     if (normalised && !d_diag) return pk_fail(PK_ERR_INVALID, "normalised Gram needs a d_diag buffer");
-    int rc = ensure_device(ctx);
-    if (rc) return rc;
+    PK_ENTER(ctx);
     std::vector<int2> tiles;
-    rc = gram_tiles(f->n, tile, part, nparts, &tiles, nullptr);
+    rc = gram_tiles(f->n, tile, part, nparts, &tiles, nullptr, f);
     if (rc) return rc;
     if (ld < f->n) return pk_fail(PK_ERR_INVALID, "gram: leading dimension smaller than N");
     if (d_diag) {   // K_ii for every tree (needed by every part for the normalisation)
@@ -1645,8 +1799,7 @@ extern "C" int pk_forest_gram_part(pk_ctx *ctx, const pk_forest *f, const pk_par
 extern "C" int pk_gram(pk_ctx *ctx, const pk_tree *const *trees, int32_t n, const pk_params *params, int normalised,
                        double *out) {
     if (!ctx || !trees || !params || !out) return pk_fail(PK_ERR_INVALID, "null argument");
-    int rc = ensure_device(ctx);
-    if (rc) return rc;
+    PK_ENTER(ctx);
     const int prec = params->precision == 32 ? 32 : 64;
     pk_forest *f = nullptr;
     rc = pk_forest_upload(ctx, trees, n, prec, &f);
@@ -1660,17 +1813,24 @@ extern "C" int pk_gram(pk_ctx *ctx, const pk_tree *const *trees, int32_t n, cons
     pk_params pp = *params;
     pp.precision = prec;
     const int32_t tile = n >= 1024 ? 32 : (n >= 128 ? 8 : 1);
-    rc = pk_forest_gram_part(ctx, f, &pp, normalised, tile, 0, 1, d_out, n, d_out + (size_t)n * n);
+    int64_t bad = 0;
+    if (prec == 32) rc = pk_ctx_nonfinite(ctx, &bad, 1);      // start counting from zero
+    if (rc == PK_OK) rc = pk_forest_gram_part(ctx, f, &pp, normalised, tile, 0, 1, d_out, n, d_out + (size_t)n * n);
     if (rc == PK_OK) {
         e = cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = pk_fail(PK_ERR_CUDA, std::string("pk_gram: ") + cudaGetErrorString(e));
     }
+    if (rc == PK_OK && prec == 32) rc = pk_ctx_nonfinite(ctx, &bad, 1);
     std::string keep = rc ? std::string(pk_last_error()) : std::string();
     cudaStreamSynchronize(ctx->stream);
     cudaFree(d_out);
     pk_forest_free(f);
     if (rc) pk_set_error(keep);
+    if (rc == PK_OK && prec == 32 && bad > 0) {      // fp32 cells overflowed somewhere: the whole matrix again in fp64 (rare)
+        pp.precision = 64;
+        return pk_gram(ctx, trees, n, &pp, normalised, out);
+    }
     return rc;
 }
 
@@ -1679,15 +1839,13 @@ extern "C" int pk_gram(pk_ctx *ctx, const pk_tree *const *trees, int32_t n, cons
 // ---------------------------------------------------------------------------------------------------
 extern "C" int pk_device_alloc(pk_ctx *ctx, size_t bytes, void **d_ptr) {
     if (!ctx || !d_ptr) return pk_fail(PK_ERR_INVALID, "null argument");
-    int rc = ensure_device(ctx);
-    if (rc) return rc;
+    PK_ENTER(ctx);
     PK_CUDA(cudaMalloc(d_ptr, bytes));
     return PK_OK;
 }
 extern "C" int pk_device_free(pk_ctx *ctx, void *d_ptr) {
     if (!ctx) return pk_fail(PK_ERR_INVALID, "null argument");
-    int rc = ensure_device(ctx);
-    if (rc) return rc;
+    PK_ENTER(ctx);
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
     PK_CUDA(cudaFree(d_ptr));
     return PK_OK;
@@ -1696,22 +1854,19 @@ extern "C" int pk_device_free(pk_ctx *ctx, void *d_ptr) {
  * a fresh pageable array costs first-touch page faults and a staged copy) */
 extern "C" int pk_host_alloc(pk_ctx *ctx, size_t bytes, void **h_ptr) {
     if (!ctx || !h_ptr) return pk_fail(PK_ERR_INVALID, "null argument");
-    int rc = ensure_device(ctx);
-    if (rc) return rc;
+    PK_ENTER(ctx);
     PK_CUDA(cudaMallocHost(h_ptr, bytes));
     return PK_OK;
 }
 extern "C" int pk_host_free(pk_ctx *ctx, void *h_ptr) {
     if (!ctx) return pk_fail(PK_ERR_INVALID, "null argument");
-    int rc = ensure_device(ctx);
-    if (rc) return rc;
+    PK_ENTER(ctx);
     PK_CUDA(cudaFreeHost(h_ptr));
     return PK_OK;
 }
 extern "C" int pk_ipc_export(pk_ctx *ctx, void *d_ptr, unsigned char handle[64]) {
     if (!ctx || !d_ptr || !handle) return pk_fail(PK_ERR_INVALID, "null argument");
-    int rc = ensure_device(ctx);
-    if (rc) return rc;
+    PK_ENTER(ctx);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t h;
     PK_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
@@ -1720,8 +1875,7 @@ extern "C" int pk_ipc_export(pk_ctx *ctx, void *d_ptr, unsigned char handle[64])
 }
 extern "C" int pk_ipc_open(pk_ctx *ctx, const unsigned char handle[64], void **d_ptr) {
     if (!ctx || !d_ptr || !handle) return pk_fail(PK_ERR_INVALID, "null argument");
-    int rc = ensure_device(ctx);
-    if (rc) return rc;
+    PK_ENTER(ctx);
     cudaIpcMemHandle_t h;
     std::memcpy(&h, handle, 64);
     PK_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
@@ -1729,32 +1883,28 @@ extern "C" int pk_ipc_open(pk_ctx *ctx, const unsigned char handle[64], void **d
 }
 extern "C" int pk_ipc_close(pk_ctx *ctx, void *d_ptr) {
     if (!ctx) return pk_fail(PK_ERR_INVALID, "null argument");
-    int rc = ensure_device(ctx);
-    if (rc) return rc;
+    PK_ENTER(ctx);
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
     PK_CUDA(cudaIpcCloseMemHandle(d_ptr));
     return PK_OK;
 }
 extern "C" int pk_memcpy_d2h(pk_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
     if (!ctx) return pk_fail(PK_ERR_INVALID, "null argument");
-    int rc = ensure_device(ctx);
-    if (rc) return rc;
+    PK_ENTER(ctx);
     PK_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
     return PK_OK;
 }
 extern "C" int pk_memcpy_h2d(pk_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
     if (!ctx) return pk_fail(PK_ERR_INVALID, "null argument");
-    int rc = ensure_device(ctx);
-    if (rc) return rc;
+    PK_ENTER(ctx);
     PK_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     PK_CUDA(cudaStreamSynchronize(ctx->stream));
     return PK_OK;
 }
 extern "C" int pk_memset_d(pk_ctx *ctx, void *d_dst, int value, size_t bytes) {
     if (!ctx) return pk_fail(PK_ERR_INVALID, "null argument");
-    int rc = ensure_device(ctx);
-    if (rc) return rc;
+    PK_ENTER(ctx);
     PK_CUDA(cudaMemsetAsync(d_dst, value, bytes, ctx->stream));
     return PK_OK;
 }

@@ -469,12 +469,14 @@ int tip_state(const char *text, const RawTree &t, int32_t v, int nstates, int &s
     while (k > 0 && p[k - 1] != '_') --k;          // token after the last '_'  (rcolgem.py:274)
     int val = 0;
     auto res = std::from_chars(p + k, p + len, val);
-    if (k == len || res.ec != std::errc() || res.ptr != p + len || val < 0 || val >= nstates) {
-        err = "tip label '" + std::string(p, len) + "' does not end in _<state> with 0 <= state < " +
+    // states are 0 .. S-1, or 1 .. S the way rcolgem numbers its demes (paste(1:n.tips, demes.sample, sep='_'),
+    // rcolgem.py:274): S is taken as state 0, so either convention maps one-to-one onto [0, S)
+    if (k == len || res.ec != std::errc() || res.ptr != p + len || val < 0 || val > nstates) {
+        err = "tip label '" + std::string(p, len) + "' does not end in _<state> with 0 <= state <= " +
               std::to_string(nstates);
         return PK_ERR_INVALID;
     }
-    state = val;
+    state = val % nstates;
     return PK_OK;
 }
 
@@ -1004,6 +1006,21 @@ extern "C" int pk_tree_from_arrays(int32_t n_internal, const int32_t *cidx, cons
 
 extern "C" void pk_tree_free(pk_tree *t) { delete t; }
 
+// The facts a tree built from arrays lacks (it has no Newick text to take them from): node heights for kcoal
+// (kamphir.py:255-258), the un-normalised height, the normalisation divisor and the tip count.  Used by the Python mirror
+// to rebuild a pickled FlatTree completely (Kamphir pickles the whole object into Pool workers, kamphir.py:27-32).
+extern "C" int pk_tree_set_heights(pk_tree *t, const double *heights, int32_t n, double height, double scale) {
+    if (!t || !heights) return pk_fail(PK_ERR_INVALID, "null argument");
+    if (n != t->n) return pk_fail(PK_ERR_INVALID, "one height per internal node expected");
+    for (int32_t i = 0; i < n; ++i)
+        if (!std::isfinite(heights[i])) return pk_fail(PK_ERR_INVALID, "non-finite node height");
+    t->heights.assign(heights, heights + n);
+    t->heights_sorted = false;
+    t->height = height;
+    t->scale = scale;
+    return PK_OK;
+}
+
 extern "C" int pk_tree_get_info(const pk_tree *t, pk_tree_info *info) {
     if (!t || !info) return pk_fail(PK_ERR_INVALID, "null argument");
     info->n_internal = t->n;
@@ -1079,6 +1096,9 @@ extern "C" int pk_kcoal(const pk_tree *sim, const pk_tree *target, double *out) 
         n1 += h * h;
         n2 += g * g;
     }
+    // all heights zero on one side: the reference divides by zero here (ZeroDivisionError at kamphir.py:269)
+    if (!(n1 > 0.0) || !(n2 > 0.0))
+        return pk_fail(PK_ERR_INVALID, "kcoal undefined: all node heights are zero (reference: ZeroDivisionError at kamphir.py:269)");
     *out = dot / (std::sqrt(n1) * std::sqrt(n2));
     return PK_OK;
 }

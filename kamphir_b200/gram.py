@@ -2,7 +2,7 @@
 (``/root/reference/phyloK2.py:148-156``).
 
 Every (i, j) entry is an independent DP, so the upper triangle is cut into tile x tile blocks that are dealt
-round-robin to the ranks (one process per GPU, ``torch.distributed``).  Each rank holds the whole packed forest
+to the ranks by cost (node pairs per tile; round-robin for equal-sized trees) (one process per GPU, ``torch.distributed``).  Each rank holds the whole packed forest
 (tens of MB) and evaluates its blocks with no data-path collective.  The only thing that crosses NVLink is the
 result:
 
@@ -65,10 +65,17 @@ class GramRunner(object):
             handle = torch.tensor(list(raw), dtype=torch.uint8)
         dev = torch.device("cuda", torch.cuda.current_device())
         h = handle.to(dev)
-        dist.broadcast(h, src=0, group=self.group)
+        dist.broadcast(h, src=self._global_rank(0), group=self.group)
         if self.rank != 0:
             raw = (ctypes.c_ubyte * 64)(*h.cpu().tolist())
             check(self.L.pk_ipc_open(self.ctx._h, raw, ctypes.byref(self.d_out)))
+
+    def _global_rank(self, r):
+        """torch.distributed takes GLOBAL ranks as src/dst, also for a sub-group."""
+        if self.group is None:
+            return r
+        import torch.distributed as dist
+        return dist.get_global_rank(self.group, r)
 
     def upload(self):
         """Host trees -> packed device forest on every rank (the H2D leg of the end-to-end path).  Returns the bytes
@@ -91,7 +98,7 @@ class GramRunner(object):
             if r == self.rank:
                 mine = nbytes
             if nbytes:
-                dist.broadcast(_as_tensor(ptr, nbytes, "|u1"), src=r, group=self.group)
+                dist.broadcast(_as_tensor(ptr, nbytes, "|u1"), src=self._global_rank(r), group=self.group)
         import torch
         torch.cuda.current_stream().synchronize()
         return mine + 32 * self.n           # + the meta records every rank uploads
@@ -114,7 +121,11 @@ class GramRunner(object):
         if self.gather == "allreduce":
             if self._torch_view is None:
                 self._torch_view = _as_tensor(self.d_local.value, self.n * self.n)
+            # the Gram kernels run on the library's stream, NCCL on torch's current stream, and fetch() copies on the
+            # library's stream again: order the three explicitly (they are the same stream only if the caller bound them)
+            self.ctx.sync()
             dist.all_reduce(self._torch_view, group=self.group)
+            torch.cuda.current_stream().synchronize()
         else:
             self.ctx.sync()                      # peer stores issued by this rank's kernel are complete
             dist.barrier(group=self.group)
@@ -131,6 +142,10 @@ class GramRunner(object):
         if not self.h_out.value:
             check(self.L.pk_host_alloc(self.ctx._h, nbytes, ctypes.byref(self.h_out)))
         check(self.L.pk_memcpy_d2h(self.ctx._h, self.h_out, self.d_local, nbytes))
+        if self.precision == 32 and self.ctx.nonfinite(reset=True):
+            # every rank counts on its own device; rank 0 sees its own tiles here, the matrix scan below sees the rest
+            raise OverflowError("fp32 cells overflowed in the Gram kernels (decayFactor too large for these trees in "
+                                "fp32): use precision=64")
         view = np.ctypeslib.as_array(ctypes.cast(self.h_out, ctypes.POINTER(ctypes.c_double)), shape=(self.n, self.n))
         return view.copy() if copy else view
 
@@ -143,20 +158,25 @@ class GramRunner(object):
         # sum over this rank's DPs of (n1 + n2): exact, from the tile assignment
         n, t = self.n, self.tile
         nint = np.array([f.n_internal for f in self.flats], dtype=np.int64)
-        nt = (n + t - 1) // t
-        k = 0
-        for ti in range(nt):
-            for tj in range(ti, nt):
-                if k % self.world == self.rank:
-                    a = nint[ti * t:min(n, (ti + 1) * t)]
-                    b = nint[tj * t:min(n, (tj + 1) * t)]
-                    if ti == tj:
-                        m = len(a)
-                        idx = np.triu_indices(m)
-                        yield int((a[idx[0]] + a[idx[1]]).sum())
-                    else:
-                        yield int(a.sum() * len(b) + b.sum() * len(a))
-                k += 1
+        for ti, tj in self.my_tiles():
+            a = nint[ti * t:min(n, (ti + 1) * t)]
+            b = nint[tj * t:min(n, (tj + 1) * t)]
+            if ti == tj:
+                m = len(a)
+                idx = np.triu_indices(m)
+                yield int((a[idx[0]] + a[idx[1]]).sum())
+            else:
+                yield int(a.sum() * len(b) + b.sum() * len(a))
+
+    def my_tiles(self):
+        """(row block, column block) of the tiles this rank evaluates for the uploaded forest (cost-weighted deal)."""
+        cnt = ctypes.c_int64(0)
+        check(self.L.pk_forest_gram_part_tiles(self.forest._h, self.tile, self.rank, self.world, None, ctypes.byref(cnt)))
+        out = np.zeros((cnt.value, 2), np.int32)
+        if cnt.value:
+            check(self.L.pk_forest_gram_part_tiles(self.forest._h, self.tile, self.rank, self.world, out.ctypes.data,
+                                                   ctypes.byref(cnt)))
+        return out
 
     def close(self):
         if self.forest is not None:

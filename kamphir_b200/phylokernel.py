@@ -34,6 +34,7 @@ class FlatTree(object):
     def __init__(self, handle, recipe):
         self._h = ctypes.c_void_p(handle)
         self._recipe = recipe
+        self._dev = None       # {(pid, device, precision): single-tree Forest}, see device_forest()
 
     def __getattr__(self, name):
         # tree facts are fetched from the library on first use (keeps bulk flattening cheap on the Python side)
@@ -126,8 +127,29 @@ class FlatTree(object):
         check(_lib.lib().pk_kcoal(self._h, target._h, ctypes.byref(out)))
         return out.value
 
+    def device_forest(self, ctx, precision=64):
+        """This tree alone as a device-resident forest, uploaded on first use and kept until the tree is dropped:
+        ``PhyloKernel.kernel(t1, t2)`` on trees it has seen before is then one launch and one copy of 8 bytes (the
+        observed tree of an MCMC run is passed to ``kernel`` 2 * nreps times per step, kamphir.py:290)."""
+        key = (os.getpid(), ctx.device, int(precision))
+        if self._dev is None:
+            self._dev = {}
+        f = self._dev.get(key)
+        if f is None or f._h is None:
+            f = Forest(ctx, [self], precision, keep=False)
+            self._dev = {k: v for k, v in self._dev.items() if k[0] == key[0]}     # a forked child drops the parent's
+            self._dev[key] = f
+        return f
+
     # -- lifetime / pickling (Kamphir dill-pickles itself into Pool workers, kamphir.py:27-32) ------------
     def __del__(self):
+        dev, self._dev = getattr(self, "_dev", None), None
+        if dev:
+            for f in dev.values():
+                try:
+                    f.close()
+                except Exception:
+                    pass
         h, self._h = getattr(self, "_h", None), None
         if h is not None and h.value:
             try:
@@ -140,17 +162,27 @@ class FlatTree(object):
         if r[0] == "newick":
             return (_rebuild_newick, r[1:])
         prod, cprod, cidx, bl = self.export()
+        # what the arrays do not carry (a tree parsed by the library from a multi-tree text keeps no text of its own):
+        # node heights for kcoal, un-normalised height, normalisation divisor
+        try:
+            extra = (self.node_heights(), float(self.height), float(self.scale))
+        except ValueError:
+            extra = None
         if self.n_states != 0:
-            return (_rebuild_arrays, (cidx, bl, prod - 1, self.n_classes))
-        return (_rebuild_arrays, (cidx, bl, None, 3))
+            return (_rebuild_arrays, (cidx, bl, prod - 1, self.n_classes, extra))
+        return (_rebuild_arrays, (cidx, bl, None, 3, extra))
 
 
 def _rebuild_newick(text, prep, normalize, n_states):
     return FlatTree.from_newick(text, prep, normalize, n_states)
 
 
-def _rebuild_arrays(cidx, bl, classes, n_classes):
-    return FlatTree.from_arrays(cidx, bl, classes, n_classes)
+def _rebuild_arrays(cidx, bl, classes, n_classes, extra=None):
+    t = FlatTree.from_arrays(cidx, bl, classes, n_classes)
+    if extra is not None:
+        h = np.ascontiguousarray(extra[0], dtype=np.float64)
+        check(_lib.lib().pk_tree_set_heights(t._h, h.ctypes.data, h.size, extra[1], extra[2]))
+    return t
 
 
 class Context(object):
@@ -184,6 +216,12 @@ class Context(object):
         return dict(ms=ms.value, launches=launches.value, path="smem" if path.value == 0 else "hbm",
                     grid=cfg[0], threads=cfg[1], smem_bytes=cfg[2])
 
+    def nonfinite(self, reset=True):
+        """Results that came out inf / NaN since the last reset (fp32 cell overflow); waits for the stream."""
+        c = ctypes.c_int64()
+        check(_lib.lib().pk_ctx_nonfinite(self._h, ctypes.byref(c), 1 if reset else 0))
+        return c.value
+
     def close(self):
         h, self._h = getattr(self, "_h", None), None
         if h is not None and h.value and self.pid == os.getpid():
@@ -199,14 +237,16 @@ class Context(object):
 class Forest(object):
     """Device-resident packed SoA of a set of FlatTrees (``pk_forest*``)."""
 
-    def __init__(self, ctx, trees, precision=64, part=None):
+    def __init__(self, ctx, trees, precision=64, part=None, keep=True):
         """part=(lo, hi): pack and upload only those trees (the rest of the device forest is filled by the other ranks,
-        see GramRunner.upload); the layout and the statistics always cover the whole set."""
+        see GramRunner.upload); the layout and the statistics always cover the whole set.  keep=False: do not hold on
+        to the FlatTrees (the device copy does not need them once it is made)."""
         self.ctx = ctx
-        self.trees = list(trees)
-        self.n = len(self.trees)
+        trees = list(trees)
+        self.trees = trees if keep else None
+        self.n = len(trees)
         self.precision = int(precision)
-        arr = (ctypes.c_void_p * self.n)(*[t._h for t in self.trees])
+        arr = (ctypes.c_void_p * self.n)(*[t._h for t in trees])
         out = ctypes.c_void_p()
         if part is None:
             check(_lib.lib().pk_forest_upload(ctx._h, arr, self.n, self.precision, ctypes.byref(out)))
@@ -237,9 +277,17 @@ class Forest(object):
         check(_lib.lib().pk_forest_pair_stats(self._h, other._h, pairs.ctypes.data, pairs.shape[0], c))
         return dict(dps=int(c[0]), node_pairs=int(c[1]), cells=int(c[2]), child_reads=int(c[3]))
 
+    def kernel_pairs(self, other, pairs, params):
+        """K for (i in self, j in other) pairs: forests stay on the device, pair list and results are host arrays."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        out = np.empty(pairs.shape[0], np.float64)
+        check(_lib.lib().pk_forest_kernel_pairs_host(self.ctx._h, self._h, other._h, pairs.ctypes.data, pairs.shape[0],
+                                                     ctypes.byref(params), out.ctypes.data))
+        return out
+
     def close(self):
         h, self._h = getattr(self, "_h", None), None
-        if h is not None and h.value and self.ctx._h is not None:
+        if h is not None and h.value and self.ctx._h is not None and self.ctx.pid == os.getpid():
             _lib.lib().pk_forest_free(h)
 
     def __del__(self):
@@ -274,7 +322,15 @@ def algorithmic_bytes(stats, precision=64):
 # the reference's class
 # ---------------------------------------------------------------------------------------------------
 class PhyloKernel(object):
-    """Drop-in for ``phyloK2.PhyloKernel`` (constructor: phyloK2.py:10-62; same keyword names and defaults)."""
+    """Drop-in for ``phyloK2.PhyloKernel`` (constructor: phyloK2.py:10-62; same keyword names and defaults).
+
+    How trees are prepared, stated once: tree OBJECTS and FlatTrees are always taken as the caller left them (the
+    reference's ``kernel`` never re-prepares, phyloK2.py:166-172).  Newick STRINGS are parsed as written by ``kernel`` /
+    ``kernel_batch`` (``prep=0, normalize='none'`` unless given), and prepared the way Kamphir prepares its trees
+    (root length 0 -> ladderize -> ``self.normalize`` -> annotate, kamphir.py:279-282) by the entry points that stand
+    for Kamphir's own loops: ``score_batch``, ``gram``, ``flatten_many``.  So for strings
+    ``gram([a, b], normalised=False)[0, 1] == kernel_batch([a], [b], prep=PK_PREP_KAMPHIR, normalize=self.normalize)[0, 0]``.
+    """
 
     def __init__(self,
                  kmat=None,
@@ -350,9 +406,11 @@ class PhyloKernel(object):
             return
         for b in targets:
             b.branch_length /= scale
+        _drop_cached_flat(t)
 
     def annotate_tree(self, t):
         """In-place annotations of phyloK2.py:132-146: production, index, bl, sqbl."""
+        _drop_cached_flat(t)
         for tip in t.get_terminals():
             tip.production = 0
         for i, node in enumerate(t.get_nonterminals(order='postorder')):
@@ -374,6 +432,13 @@ class PhyloKernel(object):
             return tree
         if isinstance(tree, (str, bytes)):
             return FlatTree.from_newick(tree, prep, normalize, self.n_states)
+        # A tree object is flattened once and the FlatTree is kept on it: the reference's kernel() reads the snapshot that
+        # annotate_tree left on the nodes (node.bl, phyloK2.py:169-172,184-185), not the live branch lengths, so the
+        # cached form stays valid until annotate_tree / normalize_tree run again (they drop it).  kamphir.py:290 passes
+        # the same observed tree 2 * nreps times per MCMC step.
+        cached = getattr(tree, '_pk_flat', None)
+        if isinstance(cached, FlatTree) and cached._h is not None:
+            return cached
         nodes = tree.get_nonterminals(order='postorder')
         if not nodes:
             raise ValueError("tree has no internal node (reference: IndexError at phyloK2.py:169)")
@@ -395,7 +460,12 @@ class PhyloKernel(object):
                 if lens[s] is None:
                     raise ValueError("branch without a length (reference: TypeError at phyloK2.py:146)")
                 bl[i, s] = lens[s]
-        return FlatTree.from_arrays(cidx, bl)
+        flat = FlatTree.from_arrays(cidx, bl)
+        try:
+            tree._pk_flat = flat
+        except AttributeError:            # an object with __slots__: nothing to hang the cache on
+            pass
+        return flat
 
     def flatten_list(self, trees, prep=0, normalize='none'):
         """flatten() for a sequence; runs of Newick strings go through one multi-threaded library call."""
@@ -427,7 +497,16 @@ class PhyloKernel(object):
         if myrank is not None and nprocs and myrank % nprocs != 0:
             k = 0.0
         else:
-            k = float(self.kernel_batch([t1], [t2], pairs=[(0, 0)])[0])
+            # single-tree forests stay on the device with their FlatTree (which stays with the tree object): a call on
+            # trees seen before is one launch plus an 8-byte copy
+            f1, f2 = self.flatten(t1), self.flatten(t2)
+            ctx = self._ctx()
+            d1 = f1.device_forest(ctx, self.precision)
+            d2 = d1 if f2 is f1 else f2.device_forest(ctx, self.precision)
+            k = float(d1.kernel_pairs(d2, _PAIR00, self._params())[0])
+            if self.precision == 32 and not math.isfinite(k):      # fp32 cells overflowed: this pair again in fp64
+                p = pk_params(float(self.decayFactor), float(self.gaussFactor), float(self.sigma), 64, 0)
+                k = float(f1.device_forest(ctx, 64).kernel_pairs(f2.device_forest(ctx, 64), _PAIR00, p)[0])
         if output is None:
             return k
         output.put(k)
@@ -436,11 +515,15 @@ class PhyloKernel(object):
         """phyloK2.py:211-236 without the processes: one GPU launch already uses the whole device."""
         return self.kernel(t1, t2)
 
-    def kernel_batch(self, trees_a, trees_b=None, pairs=None):
-        """K for many pairs in one launch.  ``pairs`` = [(ia, ib), ...] -> vector; None -> len(a) x len(b) matrix."""
-        fa = self.flatten_list(trees_a)
+    def kernel_batch(self, trees_a, trees_b=None, pairs=None, prep=0, normalize='none'):
+        """K for many pairs in one launch.  ``pairs`` = [(ia, ib), ...] -> vector; None -> len(a) x len(b) matrix.
+
+        Like ``kernel``, trees are taken as the caller prepared them: Newick strings are parsed with ``prep`` /
+        ``normalize`` (default: as written, no rescaling).  Pass ``prep=PK_PREP_KAMPHIR, normalize=self.normalize`` for
+        the preparation that ``gram`` and ``score_batch`` apply to strings (kamphir.py:279-282)."""
+        fa = self.flatten_list(trees_a, prep, normalize)
         same = trees_b is None
-        fb = fa if same else self.flatten_list(trees_b)
+        fb = fa if same else self.flatten_list(trees_b, prep, normalize)
         if pairs is None:
             pr = np.stack(np.meshgrid(np.arange(len(fa)), np.arange(len(fb)), indexing='ij'), -1).reshape(-1, 2)
         else:
@@ -501,6 +584,7 @@ class PhyloKernel(object):
             check(_lib.lib().pk_kcoal_batch(arr, n, fo._h, kc.ctypes.data))
             res['kcoal'] = kc
             res['score'] = kh * np.power(kc, 1.0 if kadj is None else kadj)
+            self._check_log_domain(res)
             res['mean_score'] = float(res['score'].sum() / n)       # kamphir.py:450
         else:
             res['mean_score'] = float(kh.sum() / n)
@@ -514,6 +598,9 @@ class PhyloKernel(object):
         if bad.size or not res['ref_denom'] > 0:
             raise ValueError("math domain error (kamphir.py:300): K = 0 for %s"
                              % ("replicate %d" % bad[0] if bad.size else "the observed tree"))
+        for key in ('knorm', 'score'):          # a NaN score would silently accept or reject an MCMC step
+            if key in res and not np.all(np.isfinite(res[key])):
+                raise ValueError("non-finite %s for replicate %d" % (key, int(np.flatnonzero(~np.isfinite(res[key]))[0])))
 
     def score_batch_sharded(self, obs, sims, rank, world, group=None, ref_denom=None, kadj=None, use_kcoal=False):
         """score_batch over the ranks of a torch.distributed group (one process per GPU): rank r scores every
@@ -559,6 +646,17 @@ class PhyloKernel(object):
                 for j in range(i, self.ntrees):
                     print('%d\t%d\t%f' % (i, j, self.kmat[i, j]))
         self.is_kmat_computed = True
+
+
+_PAIR00 = np.zeros((1, 2), np.int32)
+
+
+def _drop_cached_flat(tree):
+    try:
+        if getattr(tree, '_pk_flat', None) is not None:
+            tree._pk_flat = None
+    except AttributeError:
+        pass
 
 
 def knorm(k, ref_denom, tree_denom):

@@ -28,6 +28,8 @@ def sharded_scores(score_fn, sims, rank, world, group=None, device=None):
     """
     sims = list(sims)
     n = len(sims)
+    if n == 0:
+        raise ValueError("no simulated trees (kamphir.py:450 divides by nreps)")
     mine = shard_indices(n, rank, world)
     err = None
     try:

@@ -201,6 +201,58 @@ def kernel_arrays_labelled(A, B, decayFactor=0.1, gaussFactor=1., sigma=1.):
     return k
 
 
+def kernel_recursive(t1, t2, decayFactor=0.1, gaussFactor=1., sigma=1., states=None):
+    """The subset-tree kernel written down a second, independent way: straight from its recursive definition on the tree
+    OBJECTS, with no DP table, no flat arrays and no post-order bookkeeping (exponential in nothing, but O(n1 n2 depth):
+    for trees of a few dozen tips).  It is the checker of ``kernel_arrays`` and, above all, of the tip-state extension
+    ``kernel_arrays_labelled``, which has no reference implementation to be compared with.
+
+      K(t1, t2) = sum over internal n1 of t1, internal n2 of t2 of C(n1, n2)
+      C(n1, n2) = undefined (no match)            if the productions of n1 and n2 differ
+                = lambda * exp(-|bl(n1) - bl(n2)|^2 / tau) * prod over the child slots s = 0, 1 of
+                      sigma + lambda              both children are tips
+                      sigma + C(c1_s, c2_s)       both are internal and C of them is defined
+                      1                           otherwise
+      production of a node = number of its tip children (phyloK2.py:141-142), and, with ``states`` (tip name -> state),
+      the ordered tuple of the states of its tip children.
+    The Gaussian is written in the difference form (not the reference's expanded one), which is one more difference
+    between this function and the ones it checks; agreement is to rounding, not to the bit.
+    """
+    lam = decayFactor
+
+    def production(node):
+        tips = tuple(not c.clades for c in node.clades)
+        if states is None:
+            return sum(tips)
+        return (sum(tips), tuple(states(c.name) if not c.clades else None for c in node.clades))
+
+    def c_value(n1, n2):
+        if len(n1.clades) != 2 or len(n2.clades) != 2:
+            raise ValueError("strictly binary trees only")
+        if production(n1) != production(n2):
+            return None
+        d0 = n1.clades[0].branch_length - n2.clades[0].branch_length
+        d1 = n1.clades[1].branch_length - n2.clades[1].branch_length
+        res = lam * math.exp(-(d0 * d0 + d1 * d1) / gaussFactor)
+        for s in (0, 1):
+            c1, c2 = n1.clades[s], n2.clades[s]
+            if not c1.clades and not c2.clades:
+                res *= sigma + lam
+            elif c1.clades and c2.clades:
+                sub = c_value(c1, c2)
+                if sub is not None:
+                    res *= sigma + sub
+        return res
+
+    k = 0.0
+    for n1 in t1.get_nonterminals():
+        for n2 in t2.get_nonterminals():
+            c = c_value(n1, n2)
+            if c is not None:
+                k += c
+    return k
+
+
 def kernel(t1, t2, decayFactor=0.1, gaussFactor=1., sigma=1.):
     """Tree-object front end: annotate on the fly like ``phyloK2.py:169-172``."""
     return kernel_arrays(annotate(t1), annotate(t2), decayFactor, gaussFactor, sigma)

@@ -213,3 +213,50 @@ def test_branch_length_text_parses_like_float():
         ft = FlatTree.from_newick("(x:%s,y:%s);" % (a, b), 0, "none")
         got = np.asarray(ft.export()[-1]).ravel()
         assert got[0] == float(a) and got[1] == float(b), (a, b, got)
+
+
+def test_trees_from_multi_tree_text_pickle_completely():
+    """many_from_newick trees keep no text of their own: the pickled form carries heights, height and scale, so kcoal and
+    node_heights still work in a Pool worker (kamphir.py:27-32 pickles the whole object)."""
+    import pickle
+    nwk = synth.tree_set(5, 20, 31)
+    target = FlatTree.from_newick(synth.kingman_newick(20, 99))
+    for ft in FlatTree.many_from_newick("\n".join(nwk), 3, "mean"):
+        clone = pickle.loads(pickle.dumps(ft))
+        for x, y in zip(ft.export(), clone.export()):
+            assert np.array_equal(x, y)
+        assert np.array_equal(ft.node_heights(), clone.node_heights())
+        assert (clone.height, clone.scale, clone.n_tips) == (ft.height, ft.scale, ft.n_tips)
+        assert clone.kcoal(target) == ft.kcoal(target)
+
+
+def test_kcoal_zero_norm_is_an_error_like_the_reference():
+    # all node heights zero on one side: ZeroDivisionError at kamphir.py:269, ValueError here (never a silent NaN)
+    z = FlatTree.from_newick("((a:0,b:0):0,c:0);", 3, "none")
+    t = FlatTree.from_newick("((a:1,b:1):1,c:2);", 3, "none")
+    with pytest.raises(ValueError):
+        z.kcoal(t)
+    with pytest.raises(ValueError):
+        t.kcoal(z)
+
+
+def test_flattened_form_is_cached_on_the_tree_object_until_it_is_prepared_again():
+    """kamphir.py:290 passes the same observed tree to kernel() 2 * nreps times per step: it is walked once.  The cache
+    follows the reference's snapshot semantics (kernel() reads node.bl as annotate_tree left it, phyloK2.py:169-185):
+    normalize_tree / annotate_tree drop it."""
+    pk = PhyloKernel(decayFactor=0.2, gaussFactor=2.0)
+    t = po.read_newick(synth.kingman_newick(15, 5))
+    t.root.branch_length = 0.
+    t.ladderize()
+    pk.normalize_tree(t, "mean")
+    pk.annotate_tree(t)
+    f1 = pk.flatten(t)
+    assert pk.flatten(t) is f1
+    pk.normalize_tree(t, "median")            # rescales the live branch lengths: the snapshot is stale until annotate
+    assert getattr(t, "_pk_flat", None) is None
+    pk.annotate_tree(t)
+    f2 = pk.flatten(t)
+    assert f2 is not f1 and pk.flatten(t) is f2
+    assert not np.array_equal(f1.export()[3], f2.export()[3])
+    nodes = t.get_nonterminals(order="postorder")
+    assert f2.export()[3].tolist() == [n.bl for n in nodes]

@@ -90,3 +90,64 @@ def test_kamphir_compute_restatement():
     other = synth.kingman_newick(30, 4)
     mean2, _ = po.kamphir_evaluate([other], nwk)
     assert 0.0 < mean2 < 1.0
+
+
+def test_shipped_reference_module_reproduces_the_goldens(kat):
+    """oracle/_ref/phyloK2.py (the reference's own file, placed by oracle/Makefile; what bench.py times as the CPU
+    baseline) gives the reference's literals and the committed KAT bit for bit.  Skipped where the recipe has not run."""
+    from oracle import ref_runner as rr
+    if not rr.available():
+        pytest.skip("oracle/_ref/phyloK2.py not built (no /root/reference here)")
+    from io import StringIO
+    from Bio import Phylo
+    pk = rr.make_kernel(0.5, 1.0, 1.0)
+    t1 = Phylo.read(StringIO("( ( A:0.5, B:0.25 )E:0.5, ( C:0.25, D:0.25 )F:0.5 )G;"), "newick")
+    t2 = Phylo.read(StringIO("( ( ( A:0.25, B:0.25 )E:0.5, C:0.25 )F:0.5, D:0.25 )G;"), "newick")
+    assert pk.kernel(t1, t2) == 1.125 * (1 + math.exp(-0.0625))                  # tests/unittests.py:95
+    done = 0
+    for case in kat["cases"]:
+        if case["prep"] != "kamphir:mean" or done >= 6:
+            continue
+        a, b = case_newick(case["a"]), case_newick(case["b"])
+        if max(a.count(","), b.count(",")) > 320:
+            continue
+        pk = rr.make_kernel(case["lam"], case["tau"], case["sigma"])
+        k = pk.kernel(rr.prepare(pk, a), rr.prepare(pk, b))
+        assert k == case["K"], case["name"]
+        done += 1
+    assert done >= 3
+
+
+def test_recursive_definition_agrees_with_the_reference_literal_and_the_dp():
+    """oracle.kernel_recursive: the kernel straight from its recursive definition on tree objects (no DP table).  It
+    reproduces the reference's closed-form unit-test value and the DP restatement on random small trees."""
+    from kamphir_b200 import synth
+    k = po.kernel_recursive(po.read_newick(T1), po.read_newick(T2), 0.5, 1.0)
+    assert abs(k - 1.125 * (1 + math.exp(-0.0625))) <= 1e-15 * k                 # tests/unittests.py:95
+    for seed in range(6):
+        a = synth.kingman_newick(12 + 3 * seed, 100 + seed)
+        b = synth.yule_newick(30 - 2 * seed, 200 + seed)
+        ta, tb = po.read_newick(a), po.read_newick(b)
+        fa, fb = po.prep_kamphir(ta), po.prep_kamphir(tb)        # prepares ta, tb in place
+        want = po.kernel_arrays(fa, fb, 0.2, 2.0, 1.0)
+        got = po.kernel_recursive(ta, tb, 0.2, 2.0, 1.0)
+        assert abs(got - want) <= 1e-13 * want
+
+
+@pytest.mark.parametrize("S,prev", [(2, [0.5, 0.5]), (3, [0.2, 0.5, 0.3])])
+def test_labelled_extension_against_the_recursive_definition(S, prev):
+    """The tip-state mode has no reference implementation: its DP restatement is pinned as far as it can be,
+    against the independent recursive definition, on <= 30-tip trees with the DiffRisk / Stages state counts."""
+    from kamphir_b200 import synth
+    for seed in range(5):
+        a = synth.kingman_newick(18 + 2 * seed, 300 + seed, states=S, prevalence=prev)
+        b = synth.yule_newick(30 - seed, 400 + seed, states=S, prevalence=prev)
+        ta, tb = po.read_newick(a), po.read_newick(b)
+        fa = po.prep_kamphir(ta, "mean", po.state_from_name)
+        fb = po.prep_kamphir(tb, "mean", po.state_from_name)
+        for x, y, tx, ty in ((fa, fb, ta, tb), (fa, fa, ta, ta)):
+            want = po.kernel_arrays_labelled(x, y, 0.2, 2.0, 1.0)
+            got = po.kernel_recursive(tx, ty, 0.2, 2.0, 1.0, states=po.state_from_name)
+            assert want > 0 and abs(got - want) <= 1e-13 * want
+        # matching on is a restriction of matching off: fewer node pairs match, every C is smaller or equal
+        assert po.kernel_arrays_labelled(fa, fb, 0.2, 2.0) <= po.kernel_arrays(fa, fb, 0.2, 2.0) * (1 + 1e-12)
