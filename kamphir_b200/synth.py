@@ -153,3 +153,83 @@ def tree_set(n_trees, n_tips, base_seed, kind="mixed", states=0, prevalence=None
         else:
             out.append(yule_newick(n_tips, seed, states, prevalence))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# a minimal Bio.Phylo-shaped tree (what PhyloKernel's object path needs), for benchmarks and examples that must not
+# depend on Biopython: .root, .rooted, .clades, .branch_length, .name, get_terminals(), get_nonterminals(order)
+# ---------------------------------------------------------------------------------------------------
+class Clade(object):
+    def __init__(self, branch_length=None, name=None):
+        self.branch_length = branch_length
+        self.name = name
+        self.clades = []
+
+
+class Tree(object):
+    rooted = False
+
+    def __init__(self, root):
+        self.root = root
+
+    def _walk(self, post):
+        out, stack = [], [(self.root, False)]
+        while stack:
+            node, done = stack.pop()
+            if done or not node.clades:
+                out.append(node)
+                continue
+            if post:
+                stack.append((node, True))
+                stack.extend((c, False) for c in reversed(node.clades))
+            else:
+                out.append(node)
+                stack.extend((c, False) for c in reversed(node.clades))
+        return out
+
+    def get_terminals(self, order="preorder"):
+        return [n for n in self._walk(order == "postorder") if not n.clades]
+
+    def get_nonterminals(self, order="preorder"):
+        return [n for n in self._walk(order == "postorder") if n.clades]
+
+    def total_branch_length(self):
+        return sum(n.branch_length for n in self._walk(False) if n.branch_length)
+
+
+def newick_to_tree(text):
+    """Parse one Newick string of the dialect this module writes into a Tree of Clade objects."""
+    root = Clade()
+    node, stack, i, n = root, [], 0, len(text)
+    while i < n:
+        ch = text[i]
+        if ch == "(":
+            child = Clade()
+            node.clades.append(child)
+            stack.append(node)
+            node = child
+            i += 1
+        elif ch == ",":
+            node = Clade()
+            stack[-1].clades.append(node)
+            i += 1
+        elif ch == ")":
+            node = stack.pop()
+            i += 1
+        elif ch == ";":
+            break
+        elif ch == ":":
+            j = i + 1
+            while j < n and text[j] not in ",();":
+                j += 1
+            node.branch_length = float(text[i + 1:j])
+            i = j
+        elif ch.isspace():
+            i += 1
+        else:
+            j = i
+            while j < n and text[j] not in ":,();":
+                j += 1
+            node.name = text[i:j]
+            i = j
+    return Tree(root)

@@ -149,5 +149,8 @@ def test_labelled_extension_against_the_recursive_definition(S, prev):
             want = po.kernel_arrays_labelled(x, y, 0.2, 2.0, 1.0)
             got = po.kernel_recursive(tx, ty, 0.2, 2.0, 1.0, states=po.state_from_name)
             assert want > 0 and abs(got - want) <= 1e-13 * want
+        # the C restatement fed with classes (what the GPU tests and bench.py check the labelled mode against)
+        ca, cb = c_oracle.labelled_cflat(fa, S), c_oracle.labelled_cflat(fb, S)
+        assert abs(c_oracle.kernel(ca, cb, 0.2, 2.0) - po.kernel_arrays_labelled(fa, fb, 0.2, 2.0)) <= 1e-13 * want
         # matching on is a restriction of matching off: fewer node pairs match, every C is smaller or equal
         assert po.kernel_arrays_labelled(fa, fb, 0.2, 2.0) <= po.kernel_arrays(fa, fb, 0.2, 2.0) * (1 + 1e-12)
