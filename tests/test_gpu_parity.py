@@ -355,10 +355,15 @@ def test_gram_parts_tile_the_matrix():
         check(L.pk_memcpy_d2h(ctx._h, got.ctypes.data, d_out, 8 * n * n))
         assert not np.any((acc != 0) & (got != 0))           # disjoint
         acc += got
-        cnt = ctypes.c_int64()
-        check(L.pk_gram_part_pairs(n, 4, part, 3, ctypes.byref(cnt)))
-        assert cnt.value == forest.gram_stats(4, part, 3)["dps"] == int(np.count_nonzero(np.triu(got)))
-        total += cnt.value
+        # the forest-aware deal (by cost): its tile list, its DP count and what the kernel wrote agree
+        nt = ctypes.c_int64(0)
+        check(L.pk_forest_gram_part_tiles(forest._h, 4, part, 3, None, ctypes.byref(nt)))
+        tiles = np.zeros((nt.value, 2), np.int32)
+        check(L.pk_forest_gram_part_tiles(forest._h, 4, part, 3, tiles.ctypes.data, ctypes.byref(nt)))
+        dps = sum((min(n, 4 * ti + 4) - 4 * ti) * (min(n, 4 * tj + 4) - 4 * tj) if ti != tj
+                  else (min(n, 4 * ti + 4) - 4 * ti) * (min(n, 4 * ti + 4) - 4 * ti + 1) // 2 for ti, tj in tiles)
+        assert dps == forest.gram_stats(4, part, 3)["dps"] == int(np.count_nonzero(np.triu(got)))
+        total += dps
     assert total == n * (n + 1) // 2 and np.array_equal(acc, full)
     check(L.pk_device_free(ctx._h, d_out))
     check(L.pk_device_free(ctx._h, d_diag))
