@@ -51,6 +51,7 @@ SIGNATURES = {
     "pk_ctx_set_stream": (ctypes.c_int, [_P, _P]),
     "pk_ctx_sync": (ctypes.c_int, [_P]),
     "pk_ctx_configure": (ctypes.c_int, [_P, _I32, _I32, _I32]),
+    "pk_ctx_set_option": (ctypes.c_int, [_P, ctypes.c_char_p, _I32]),
     "pk_ctx_last_stats": (ctypes.c_int, [_P, ctypes.POINTER(_D), ctypes.POINTER(_I64), ctypes.POINTER(_I32), _P]),
     "pk_ctx_nonfinite": (ctypes.c_int, [_P, ctypes.POINTER(_I64), ctypes.c_int]),
     "pk_forest_upload": (ctypes.c_int, [_P, _P, _I32, _I32, _PP]),

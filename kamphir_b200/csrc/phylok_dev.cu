@@ -74,6 +74,8 @@ struct DpArgs {
     int tree_region;                // shared-memory bytes reserved for the staged ROW part
     int col_region;                 // ... and for the staged COLUMN part
     int rowinfo_bytes;              // row offsets
+    unsigned char *stage;           // STAGED = false: per-CTA staging area in global memory (tree parts + row offsets)
+    long long stage_stride;
     double bscale;                  // sqrt(64 / (ln2 tau)) (fp64) or sqrt(1 / (ln2 tau)) (fp32), applied to the staged branch lengths
     int clamp_hi;                   // fp64 Gaussian: clamp of the exponent's high word
     unsigned long long exp_tab[64]; // fp64 Gaussian: bits of lambda * 2^(j/64) with the high word biased by -(j << 14)
@@ -263,9 +265,13 @@ struct Cells {
 // gathers that skip the mismatching lanes, gathers two groups ahead: all slower, the loop is sensitive to instruction
 // count and registers.)  Returns the column's partial sum of C over the rows.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int4 lds_int4(const int4 *p) {     // always one LDS.128 (never split into scalar loads)
+template <bool STAGED>
+__device__ __forceinline__ int4 ld_int4(const int4 *p) {
     int4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
+    if (STAGED)      // always one LDS.128 (never split into scalar loads)
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
+    else             // parts staged in global memory (trees beyond the shared-memory limit): one uniform 16-byte load, L1-resident
+        asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
 
@@ -288,7 +294,7 @@ __device__ __forceinline__ int4 lds_int4(const int4 *p) {     // always one LDS.
 // child cell of slot 0 / 1: the stored cell when the children's classes agree, else cell 1 (= 1, productions differ)
 #define PK_GATHER0(q) C.ld((((q).w ^ qb0) & 0xff) == 0 ? (q).x + kb0 : 1)
 #define PK_GATHER1(q) C.ld((((q).w ^ qb1) & 0xff00) == 0 ? (q).y + kb1 : 1)
-template <typename T, bool CSMEM, bool G0, bool G1, int U, bool FENCE, bool OVRQ>
+template <typename T, bool CSMEM, bool STAGED, bool G0, bool G1, int U, bool FENCE, bool OVRQ>
 __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0, T b1, int cb0, int cb1, int pkey,
                                      const Cells<T, CSMEM> &C, const GaussK<T> &gk, T sigma, T tipf) {
     constexpr bool OVR = OVRQ && !CSMEM;         // the prefetch may run past the rectangle (see PK_OVERRUN)
@@ -308,7 +314,7 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
     if ((G0 || G1) && U <= rows) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int4 q = lds_int4(ip + 2 * u + 1);
+            const int4 q = ld_int4<STAGED>(ip + 2 * u + 1);
             if (G0) f0[u] = PK_GATHER0(q);
             if (G1) f1[u] = PK_GATHER1(q);
         }
@@ -325,7 +331,7 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
             const int4 *np = OVR || rr + 2 * U <= rows ? ip + 2 * U : ip;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int4 q = lds_int4(np + 2 * u + 1);
+                const int4 q = ld_int4<STAGED>(np + 2 * u + 1);
                 if (G0) f0[u] = PK_GATHER0(q);
                 if (G1) f1[u] = PK_GATHER1(q);
             }
@@ -355,7 +361,7 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
 #pragma unroll
             for (int u = 0; u < U - 1; ++u) {
                 if (u < rem) {
-                    const int4 q = lds_int4(ip + 2 * u + 1);
+                    const int4 q = ld_int4<STAGED>(ip + 2 * u + 1);
                     if (G0) f0[u] = PK_GATHER0(q);
                     if (G1) f1[u] = PK_GATHER1(q);
                 }
@@ -397,7 +403,10 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
 // (pairs) being resident per SM.
 // DEAL: the 32-column chunks of all rectangles of a level are dealt to the warps (labelled trees: many narrow classes);
 // otherwise thread t owns column t of every rectangle and the rectangles of a level run one after the other.
-template <typename T, bool CSMEM, int BOUND, bool DEAL>     // BOUND: upper bound of the CTA size (sets the register budget)
+// STAGED = false: trees whose parts do not fit the shared memory of an SM.  The parts are copied into a per-CTA area in
+// global memory instead, patched there and read through L1 (uniform row records, once-per-rectangle column data): the
+// reference has no size limit (phyloK2.py:158-209), and neither has this path.
+template <typename T, bool CSMEM, int BOUND, bool DEAL, bool STAGED>     // BOUND: upper bound of the CTA size (sets the register budget)
 #ifndef PK_MINB192
 #define PK_MINB192 5
 #endif
@@ -439,10 +448,11 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 64    ? (sizeof(T) == 4 ? 16 
     int tid;                                                   // opaque read: lives in a register, never re-read via S2R
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
     const int lane = tid & 31, warp = tid >> 5;
-    unsigned char *sA = smem;                                  // ROW part of the row tree (its records are patched in place)
-    unsigned char *sB = smem + a.tree_region;                  // COLUMN part of the column tree
+    unsigned char *const stage = STAGED ? smem : a.stage + (size_t)blockIdx.x * (size_t)a.stage_stride;
+    unsigned char *sA = stage;                                 // ROW part of the row tree (its records are patched in place)
+    unsigned char *sB = stage + a.tree_region;                 // COLUMN part of the column tree
     const size_t info_at = (size_t)a.tree_region + a.col_region;
-    int *rowoff = reinterpret_cast<int *>(smem + info_at);
+    int *rowoff = reinterpret_cast<int *>(stage + info_at);
     const unsigned long long slab_off = (unsigned long long)blockIdx.x * (unsigned long long)a.slab_elems;
     Cells<T, CSMEM> cells;
     cells.sm = reinterpret_cast<T *>(smem + info_at + a.rowinfo_bytes);
@@ -501,15 +511,22 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 64    ? (sizeof(T) == 4 ? 16 
         const uint32_t bytesR = mR.y, bytesC = mC.y;
 
         // ---- stage both node blocks with TMA bulk copies ---------------------------------------
-        if (tid == 0) {
-            // the staging buffers were last written through the generic proxy (record patch, length scale, pad records)
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&s_bar, bytesR + bytesC);
-            tma_bulk_g2s(sA, srcR, bytesR, &s_bar);
-            tma_bulk_g2s(sB, srcC, bytesC, &s_bar);
+        if (STAGED) {
+            if (tid == 0) {
+                // the staging buffers were last written through the generic proxy (record patch, length scale, pad records)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&s_bar, bytesR + bytesC);
+                tma_bulk_g2s(sA, srcR, bytesR, &s_bar);
+                tma_bulk_g2s(sB, srcC, bytesC, &s_bar);
+            }
+            mbar_wait(&s_bar, parity);
+            parity ^= 1;
+        } else {
+            // this CTA's private copies in global memory (the forest itself stays untouched: the records are patched per pair)
+            for (uint32_t i = tid; i < bytesR / 16; i += NT) reinterpret_cast<int4 *>(sA)[i] = reinterpret_cast<const int4 *>(srcR)[i];
+            for (uint32_t i = tid; i < bytesC / 16; i += NT) reinterpret_cast<int4 *>(sB)[i] = reinterpret_cast<const int4 *>(srcC)[i];
+            __syncthreads();
         }
-        mbar_wait(&s_bar, parity);
-        parity ^= 1;
         if (OVRQ && !CSMEM && tid < PK_PAD_RECORDS) {     // never-matching records after the last row (see PK_OVERRUN)
             int4 *padrec = reinterpret_cast<int4 *>(sA + bytesR) + 2 * tid;
             padrec[0] = make_int4(0, 0, 0, 0);
@@ -619,19 +636,19 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 64    ? (sizeof(T) == 4 ? 16 
         T part;                                                                                                       \
         switch ((D).flags & (512 | 1024)) {               /* bit 9 / 10: slot 0 / 1 is a tip in every row of the class */ \
         case 512 | 1024:                                                                                              \
-            part = pk_rect<T, CSMEM, false, false, U, DEAL || PK_FENCE_ALL, OVRQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,   \
+            part = pk_rect<T, CSMEM, STAGED, false, false, U, DEAL || PK_FENCE_ALL, OVRQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,   \
                                                             cells, gk, sigma, tipf);                                  \
             break;                                                                                                    \
         case 512:                                                                                                     \
-            part = pk_rect<T, CSMEM, false, true, U, DEAL || PK_FENCE_ALL, OVRQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,    \
+            part = pk_rect<T, CSMEM, STAGED, false, true, U, DEAL || PK_FENCE_ALL, OVRQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,    \
                                                            cells, gk, sigma, tipf);                                   \
             break;                                                                                                    \
         case 1024:                                                                                                    \
-            part = pk_rect<T, CSMEM, true, false, U, DEAL || PK_FENCE_ALL, OVRQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,    \
+            part = pk_rect<T, CSMEM, STAGED, true, false, U, DEAL || PK_FENCE_ALL, OVRQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,    \
                                                            cells, gk, sigma, tipf);                                   \
             break;                                                                                                    \
         default:                                                                                                      \
-            part = pk_rect<T, CSMEM, true, true, U, DEAL || PK_FENCE_ALL, OVRQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,     \
+            part = pk_rect<T, CSMEM, STAGED, true, true, U, DEAL || PK_FENCE_ALL, OVRQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,     \
                                                           cells, gk, sigma, tipf);                                    \
         }                                                                                                             \
         acc += (double)part;                                                                                          \
@@ -723,6 +740,7 @@ struct pk_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     int cfg_threads = 0, cfg_ctas = 0, cfg_force_hbm = 0;
+    int opt_unstaged = 0;                       // 1: stage the tree parts in global memory even when they would fit (tests)
     void *d_scratch = nullptr;
     size_t scratch_bytes = 0;
     unsigned long long *d_counters = nullptr;   // ring of work counters (one per launch in flight)
@@ -892,6 +910,14 @@ extern "C" int pk_ctx_configure(pk_ctx *ctx, int32_t threads, int32_t ctas_per_s
     ctx->cfg_threads = threads;
     ctx->cfg_ctas = ctas_per_sm;
     ctx->cfg_force_hbm = force_hbm;
+    return PK_OK;
+}
+
+extern "C" int pk_ctx_set_option(pk_ctx *ctx, const char *name, int32_t value) {
+    if (!ctx || !name) return pk_fail(PK_ERR_INVALID, "null argument");
+    const std::string key(name);
+    if (key == "unstaged") ctx->opt_unstaged = value ? 1 : 0;
+    else return pk_fail(PK_ERR_INVALID, "unknown option '" + key + "'");
     return PK_OK;
 }
 
@@ -1186,35 +1212,35 @@ extern "C" int pk_forest_pair_stats(const pk_forest *fa, const pk_forest *fb, co
 // ---------------------------------------------------------------------------------------------------
 // The dynamic shared-memory limit of a kernel variant is raised once per size and its occupancy is queried once per
 // (CTA size, shared memory): a sim-vs-obs proposal is one 30 us launch, the driver calls would cost more than that.
-template <typename T, bool CSMEM, int BOUND, bool DEAL>
+template <typename T, bool CSMEM, int BOUND, bool DEAL, bool STAGED>
 static cudaError_t launch_t(pk_ctx *ctx, const DpArgs &args, int grid, int nt, int smem, cudaStream_t stream) {
-    int &have = ctx->attr_smem[{(int)sizeof(T) + 16 * (int)DEAL, (int)CSMEM, BOUND}];
+    int &have = ctx->attr_smem[{(int)sizeof(T) + 16 * (int)DEAL + 32 * (int)STAGED, (int)CSMEM, BOUND}];
     if (smem > have) {
-        cudaError_t e =
-            cudaFuncSetAttribute(pk_dp_kernel<T, CSMEM, BOUND, DEAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(pk_dp_kernel<T, CSMEM, BOUND, DEAL, STAGED>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         have = smem;
     }
-    pk_dp_kernel<T, CSMEM, BOUND, DEAL><<<grid, nt, smem, stream>>>(args);
+    pk_dp_kernel<T, CSMEM, BOUND, DEAL, STAGED><<<grid, nt, smem, stream>>>(args);
     return cudaGetLastError();
 }
 
-template <typename T, bool CSMEM, int BOUND, bool DEAL>
+template <typename T, bool CSMEM, int BOUND, bool DEAL, bool STAGED>
 static cudaError_t occupancy_t(pk_ctx *ctx, int nt, int smem, int *blocks) {
-    auto key = std::make_tuple((int)sizeof(T) + 16 * (int)DEAL, (int)CSMEM, BOUND, nt, smem);
+    auto key = std::make_tuple((int)sizeof(T) + 16 * (int)DEAL + 32 * (int)STAGED, (int)CSMEM, BOUND, nt, smem);
     auto it = ctx->occupancy.find(key);
     if (it != ctx->occupancy.end()) {
         *blocks = it->second;
         return cudaSuccess;
     }
-    int &have = ctx->attr_smem[{(int)sizeof(T) + 16 * (int)DEAL, (int)CSMEM, BOUND}];
+    int &have = ctx->attr_smem[{(int)sizeof(T) + 16 * (int)DEAL + 32 * (int)STAGED, (int)CSMEM, BOUND}];
     if (smem > have) {
-        cudaError_t e =
-            cudaFuncSetAttribute(pk_dp_kernel<T, CSMEM, BOUND, DEAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(pk_dp_kernel<T, CSMEM, BOUND, DEAL, STAGED>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         have = smem;
     }
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, pk_dp_kernel<T, CSMEM, BOUND, DEAL>, nt, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, pk_dp_kernel<T, CSMEM, BOUND, DEAL, STAGED>, nt, smem);
     if (e == cudaSuccess) ctx->occupancy[key] = *blocks;
     return e;
 }
@@ -1224,19 +1250,22 @@ static cudaError_t occupancy_t(pk_ctx *ctx, int nt, int smem, int *blocks) {
 // <= 384: 80 (2 CTAs), <= 576: 56 (2 CTAs; 1500 tips: 432 against 378 with one CTA), <= 512: 64 (2 CTAs; one CTA of 128 registers ran 5 %
 // (fp64) / 37 % (fp32) slower at 1300 tips), <= 768: 80, else 64 (one CTA per SM)
 #define PK_DISPATCH_NT(FN, TT, CS, DL, ...)                                                     \
-    (nt <= 64    ? FN<TT, CS, 64, DL>(__VA_ARGS__)                                              \
-     : nt <= 192 ? FN<TT, CS, 192, DL>(__VA_ARGS__)                                           \
-     : nt <= 224 ? FN<TT, CS, 224, DL>(__VA_ARGS__)                                             \
-     : nt <= 256 ? FN<TT, CS, 256, DL>(__VA_ARGS__)                                             \
-     : nt <= 320 ? FN<TT, CS, 320, DL>(__VA_ARGS__)                                             \
-     : nt <= 352 ? FN<TT, CS, 352, DL>(__VA_ARGS__)                                             \
-     : nt <= 384 ? FN<TT, CS, 384, DL>(__VA_ARGS__)                                             \
-     : nt <= 512 ? FN<TT, CS, 512, DL>(__VA_ARGS__)                                             \
-     : nt <= 576 ? FN<TT, CS, 576, DL>(__VA_ARGS__)                                             \
-     : nt <= 768 ? FN<TT, CS, 768, DL>(__VA_ARGS__)                                             \
-                 : FN<TT, CS, 1024, DL>(__VA_ARGS__))
-#define PK_DISPATCH_CS(FN, TT, DL, ...) \
-    (csmem ? PK_DISPATCH_NT(FN, TT, true, DL, __VA_ARGS__) : PK_DISPATCH_NT(FN, TT, false, DL, __VA_ARGS__))
+    (nt <= 64    ? FN<TT, CS, 64, DL, true>(__VA_ARGS__)                                              \
+     : nt <= 192 ? FN<TT, CS, 192, DL, true>(__VA_ARGS__)                                           \
+     : nt <= 224 ? FN<TT, CS, 224, DL, true>(__VA_ARGS__)                                             \
+     : nt <= 256 ? FN<TT, CS, 256, DL, true>(__VA_ARGS__)                                             \
+     : nt <= 320 ? FN<TT, CS, 320, DL, true>(__VA_ARGS__)                                             \
+     : nt <= 352 ? FN<TT, CS, 352, DL, true>(__VA_ARGS__)                                             \
+     : nt <= 384 ? FN<TT, CS, 384, DL, true>(__VA_ARGS__)                                             \
+     : nt <= 512 ? FN<TT, CS, 512, DL, true>(__VA_ARGS__)                                             \
+     : nt <= 576 ? FN<TT, CS, 576, DL, true>(__VA_ARGS__)                                             \
+     : nt <= 768 ? FN<TT, CS, 768, DL, true>(__VA_ARGS__)                                             \
+                 : FN<TT, CS, 1024, DL, true>(__VA_ARGS__))
+// unstaged: trees beyond the shared-memory staging limit (parts in a per-CTA global area, C in HBM slabs, 1024-thread tier)
+#define PK_DISPATCH_CS(FN, TT, DL, ...)                          \
+    (unstaged ? FN<TT, false, 1024, DL, false>(__VA_ARGS__)      \
+     : csmem  ? PK_DISPATCH_NT(FN, TT, true, DL, __VA_ARGS__)    \
+              : PK_DISPATCH_NT(FN, TT, false, DL, __VA_ARGS__))
 #define PK_DISPATCH(FN, ...)                                                                                \
     (prec32 ? (deal ? PK_DISPATCH_CS(FN, float, true, __VA_ARGS__) : PK_DISPATCH_CS(FN, float, false, __VA_ARGS__)) \
             : (deal ? PK_DISPATCH_CS(FN, double, true, __VA_ARGS__) : PK_DISPATCH_CS(FN, double, false, __VA_ARGS__)))
@@ -1312,9 +1341,8 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
     const int rowinfo = ((max_n * 4) + 127) & ~127;                          // row offsets
     const long long base_smem = (long long)region_r + region_c + rowinfo;
     const long long limit = ctx->smem_optin - 16384;   // static shared memory (table, level descriptors, ...)
-    if (base_smem > limit)
-        return pk_fail(PK_ERR_INVALID, "trees too large to stage in shared memory (" + std::to_string(base_smem) +
-                                           " bytes needed, " + std::to_string(limit) + " available)");
+    // trees too large to stage in shared memory (~3 500 tips): their parts are staged in a per-CTA area in global memory
+    const bool unstaged = base_smem > limit || ctx->opt_unstaged;
     const long long c_bytes = ((maxM * (long long)w) + 127) & ~127ll;
     args.tree_region = region_r;
     args.col_region = region_c;
@@ -1340,9 +1368,9 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
     // C in shared memory only when that costs no resident CTAs: with C in a global slab the CTAs of small pairs stay
     // L2-resident anyway and more pairs per SM hide the level barriers better (measured: profiles/r01_summary.md)
     bool csmem = false;
-    int smem = (int)base_smem, per_sm = 0;
+    int smem = unstaged ? 0 : (int)base_smem, per_sm = 0;
     cudaError_t e = PK_DISPATCH(occupancy_t, ctx, nt, smem, &per_sm);
-    if (e == cudaSuccess && ctx->cfg_force_hbm != 1 && base_smem + c_bytes <= limit) {
+    if (e == cudaSuccess && !unstaged && ctx->cfg_force_hbm != 1 && base_smem + c_bytes <= limit) {
         int occ_smem = 0;
         csmem = true;
         e = PK_DISPATCH(occupancy_t, ctx, nt, (int)(base_smem + c_bytes), &occ_smem);
@@ -1363,9 +1391,13 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
         if (PK_OVERRUN)
             for (size_t g = 0; g < fa->max_gcnt.size(); ++g) slack = std::max<long long>(slack, std::max(fa->max_gcnt[g], fb->max_gcnt[g]));
         args.slab_elems = ((((maxM + slack) * (long long)w) + 255) & ~255ll) / (long long)w;
-        int rc = ensure_scratch(ctx, (size_t)grid * (size_t)args.slab_elems * w);
+        // the slabs, then (unstaged) one staging area per CTA
+        const size_t slab_bytes = ((size_t)grid * (size_t)args.slab_elems * w + 255) & ~(size_t)255;
+        args.stage_stride = unstaged ? (long long)((base_smem + 255) & ~255ll) : 0;
+        int rc = ensure_scratch(ctx, slab_bytes + (size_t)grid * (size_t)args.stage_stride);
         if (rc) return rc;
         args.scratch = ctx->d_scratch;
+        args.stage = static_cast<unsigned char *>(ctx->d_scratch) + slab_bytes;
     }
 #ifdef PK_DEBUG_BOUNDS
     if (csmem) args.slab_elems = c_bytes / (long long)w;                      // the limit the cell indices are checked against
@@ -1390,7 +1422,7 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
 #endif
     ctx->ev_valid = true;
     ctx->launches++;
-    ctx->last_path = csmem ? 0 : 1;
+    ctx->last_path = csmem ? 0 : (unstaged ? 2 : 1);
     ctx->last_grid = grid;
     ctx->last_threads = nt;
     ctx->last_smem = smem;

@@ -199,9 +199,14 @@ class Context(object):
         force = int(os.environ.get("PK_FORCE_HBM", "0"))
         if threads or ctas or force:
             self.configure(threads, ctas, force)
+        if os.environ.get("PK_UNSTAGED"):
+            self.set_option("unstaged", int(os.environ["PK_UNSTAGED"]))
 
     def configure(self, threads=0, ctas_per_sm=0, force_hbm=0):
         check(_lib.lib().pk_ctx_configure(self._h, int(threads), int(ctas_per_sm), int(force_hbm)))
+
+    def set_option(self, name, value):
+        check(_lib.lib().pk_ctx_set_option(self._h, name.encode(), int(value)))
 
     def set_stream(self, cuda_stream):
         check(_lib.lib().pk_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream) if cuda_stream else None))
@@ -213,7 +218,8 @@ class Context(object):
         ms, launches, path = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int32()
         cfg = (ctypes.c_int32 * 3)()
         check(_lib.lib().pk_ctx_last_stats(self._h, ctypes.byref(ms), ctypes.byref(launches), ctypes.byref(path), cfg))
-        return dict(ms=ms.value, launches=launches.value, path="smem" if path.value == 0 else "hbm",
+        return dict(ms=ms.value, launches=launches.value,
+                    path={0: "smem", 1: "hbm", 2: "hbm-unstaged"}.get(path.value, "hbm"),
                     grid=cfg[0], threads=cfg[1], smem_bytes=cfg[2])
 
     def nonfinite(self, reset=True):

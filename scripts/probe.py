@@ -1,5 +1,6 @@
 """Quick device-side timing probe (not the benchmark): Gram part over n trees for several launch configurations."""
 import ctypes
+import os
 import sys
 import time
 
@@ -18,6 +19,8 @@ def main():
     states = int(sys.argv[5]) if len(sys.argv) > 5 else 0      # tip states (BASELINE.json configs[2]): labelled productions
     t0 = time.time()
     nwk = synth.tree_set(n, tips, 3000, "mixed", states, [1.0 / states] * states if states else None)
+    if os.environ.get("PK_PROBE_SAME"):          # n copies of one tree: every pair has the forest's maximal group sizes
+        nwk = [nwk[0]] * n
     flats = FlatTree.many_from_newick("\n".join(nwk), 3, "mean", states)
     print("gen+flatten %.2fs" % (time.time() - t0), flush=True)
     ctx = get_context(0)

@@ -240,3 +240,41 @@ def test_cost_weighted_gram_parts_cover_the_triangle_and_balance_ragged_forests(
     # every entry is written by exactly one part (the others left zeros): the sum is the matrix
     assert rel(full, want) <= 1e-9
     assert max(loads) <= 1.25 * (sum(loads) / world)          # round-robin on this forest: 1.6
+
+
+# ---------------------------------------------------------------------------------------------------
+# kernel variant of round 2: tree parts left in global memory (trees beyond the shared-memory staging limit)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision,states", [(64, 0), (32, 0), (64, 3)])
+def test_tree_parts_left_in_global_memory(precision, states):
+    """The variant for trees beyond the shared-memory staging limit, forced on ordinary trees: identical results."""
+    nwk = [synth.kingman_newick(90 + 20 * i, 9500 + i, states=states) for i in range(5)]
+    flats = [FlatTree.from_newick(s, 3, "mean", states) for s in nwk]
+    pk = PhyloKernel(precision=precision, n_states=states, **KAM)
+    ctx = get_context()
+    staged = pk.kernel_batch(flats)
+    try:
+        ctx.set_option("unstaged", 1)
+        unstaged = pk.kernel_batch(flats)
+        assert ctx.last_stats()["path"] == "hbm-unstaged"
+        g = pk.gram(flats, normalised=False)
+    finally:
+        ctx.set_option("unstaged", 0)
+    assert np.array_equal(unstaged, staged)
+    assert rel(g, staged) <= (1e-12 if precision == 64 else 1e-6)      # the Gram form evaluates (i, j) once and mirrors it
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+def test_5000_tip_pair_beyond_the_staging_limit(precision):
+    """Round 1 rejected trees whose packed parts exceed the shared memory of an SM (~3 500 tips); the reference has no size
+    limit (phyloK2.py:158-209).  5 000 tips against 5 000 and against 3 000, checked against the C oracle."""
+    a, b, c = synth.kingman_newick(5000, 9700), synth.yule_newick(5000, 9701), synth.kingman_newick(3000, 9702)
+    pk = PhyloKernel(precision=precision, **KAM)
+    fa, fb, fc = FlatTree.from_newick(a), FlatTree.from_newick(b), FlatTree.from_newick(c)
+    got = pk.kernel_batch([fa, fb, fc], pairs=[(0, 1), (0, 0), (2, 1)])
+    assert get_context().last_stats()["path"] == "hbm-unstaged"
+    oa, ob, oc = oracle_flat(a), oracle_flat(b), oracle_flat(c)
+    want = [c_oracle.kernel(oa, ob, 0.2, 2.0), c_oracle.kernel(oa, oa, 0.2, 2.0), c_oracle.kernel(oc, ob, 0.2, 2.0)]
+    assert rel(got, want) <= TOL[precision]
+    res = pk.score_batch(a, [b, c])
+    assert abs(res["knorm"][0] - want[0] / math.sqrt(want[1] * c_oracle.kernel(ob, ob, 0.2, 2.0))) <= 10 * TOL[precision]
