@@ -1035,12 +1035,18 @@ static int forest_upload_impl(pk_ctx *ctx, const pk_tree *const *trees, int32_t 
     if (precision != 64 && precision != 32) return pk_fail(PK_ERR_INVALID, "precision must be 64 or 32");
     *out = nullptr;
     PK_ENTER(ctx);
+    static const bool trace = std::getenv("PK_TRACE") != nullptr;      // PK_TRACE=1: per-phase host times on stderr
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = trace ? now() : 0.0;
     const int ncls = trees[0] ? trees[0]->ncls : 0;
     size_t total = 0;
+    std::vector<uint32_t> rbs((size_t)n), cbs((size_t)n);      // part sizes, computed once per tree
     for (int32_t i = 0; i < n; ++i) {
         if (!trees[i]) return pk_fail(PK_ERR_INVALID, "null tree in set");
         if (trees[i]->ncls != ncls) return pk_fail(PK_ERR_INVALID, "trees use different production class schemes");
-        total += pk_rowpart_bytes(*trees[i], precision) + pk_colpart_bytes(*trees[i], precision);
+        rbs[i] = (uint32_t)pk_rowpart_bytes(*trees[i], precision);
+        cbs[i] = (uint32_t)pk_colpart_bytes(*trees[i], precision);
+        total += (size_t)rbs[i] + cbs[i];
     }
     if (total / 16 > 0x7fffffffull) return pk_fail(PK_ERR_INVALID, "tree set too large for one forest");
     const int npc = 2 * ncls + 2;
@@ -1068,23 +1074,23 @@ static int forest_upload_impl(pk_ctx *ctx, const pk_tree *const *trees, int32_t 
     unsigned char *h = static_cast<unsigned char *>(ctx->h_pinned);
     int4 *hmeta = reinterpret_cast<int4 *>(h + total);
     std::vector<size_t> offs((size_t)n + 1, 0);
-    for (int32_t i = 0; i < n; ++i)
-        offs[i + 1] = offs[i] + pk_rowpart_bytes(*trees[i], precision) + pk_colpart_bytes(*trees[i], precision);
+    for (int32_t i = 0; i < n; ++i) offs[i + 1] = offs[i] + rbs[i] + cbs[i];
     // packing writes every byte of the forest once (125 MB for 4096 x 500 tips): spread it over the host cores
     auto pack_range = [&](int32_t lo, int32_t hi) {
         for (int32_t i = lo; i < hi; ++i) {
             const pk_tree &t = *trees[i];
-            const size_t off = offs[i], rb = pk_rowpart_bytes(t, precision);
+            const size_t off = offs[i], rb = rbs[i];
             pk_rowpart_pack(t, precision, h + off);
             pk_colpart_pack(t, precision, h + off + rb);
         }
     };
     for (int32_t i = 0; i < n; ++i) {
         const pk_tree &t = *trees[i];
-        const size_t off = offs[i], rb = pk_rowpart_bytes(t, precision), cb = pk_colpart_bytes(t, precision);
+        const size_t off = offs[i], rb = rbs[i], cb = cbs[i];
         hmeta[2 * i] = make_int4((int)(off / 16), (int)rb, t.n, t.nlev);            // row part
         hmeta[2 * i + 1] = make_int4((int)((off + rb) / 16), (int)cb, t.n, t.nlev);   // column part
     }
+    const double t1 = trace ? now() : 0.0;
     // Device buffer first, then pack and copy in phases: while the cores pack phase p + 1 into the pinned buffer, the
     // copy engine moves phase p (a 31 MB forest of 256 x 2000-tip trees: ~1.3 ms of copy hidden behind the packing).
     void *dptr = nullptr;
@@ -1114,27 +1120,45 @@ static int forest_upload_impl(pk_ctx *ctx, const pk_tree *const *trees, int32_t 
         }
         if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_meta, hmeta, meta_bytes, cudaMemcpyHostToDevice, ctx->stream);
     }
-    for (int32_t i = 0; i < n; ++i) {
-        const pk_tree &t = *trees[i];
-        const size_t rb = pk_rowpart_bytes(t, precision), cb = pk_colpart_bytes(t, precision);
-        f->max_rowpart = std::max<int32_t>(f->max_rowpart, (int32_t)rb);
-        f->max_colpart = std::max<int32_t>(f->max_colpart, (int32_t)cb);
-        f->max_n = std::max(f->max_n, t.n);
-        f->nint[i] = t.n;
-        for (int c = 0; c < ncls; ++c) {
-            int cnt = t.cls_start[c + 1] - t.cls_start[c];
-            f->cnt[(size_t)i * ncls + c] = cnt;
-            f->max_cnt[c] = std::max(f->max_cnt[c], cnt);
-            f->tree_w[i] = std::max(f->tree_w[i], cnt);
+    const double t2 = trace ? now() : 0.0;
+    // host-side statistics of every tree of the set (this rank's part or not): per-tree entries in parallel, maxima after
+    {
+        const int nthr = (int)std::min<size_t>(std::min(pk_host_threads(), 16), std::max<size_t>(1, (size_t)n / 256));
+        std::atomic<int32_t> next{0};
+        pk_parallel(nthr, [&](int) {
+            for (;;) {
+                const int32_t lo = next.fetch_add(64);
+                if (lo >= n) break;
+                for (int32_t i = lo; i < std::min(n, lo + 64); ++i) {
+                    const pk_tree &t = *trees[i];
+                    f->nint[i] = t.n;
+                    int32_t wmax = 1;
+                    for (int c = 0; c < ncls; ++c) {
+                        const int cnt = t.cls_start[c + 1] - t.cls_start[c];
+                        f->cnt[(size_t)i * ncls + c] = cnt;
+                        wmax = std::max(wmax, cnt);
+                    }
+                    f->tree_w[i] = wmax;
+                    for (int g = 0; g < ncls * npc; ++g) f->gcnt[(size_t)i * ncls * npc + g] = t.gstart[g + 1] - t.gstart[g];
+                    std::copy(t.hist.begin(), t.hist.end(), f->hist.begin() + (size_t)i * t.hist.size());
+                }
+            }
+        });
+        for (int32_t i = 0; i < n; ++i) {
+            f->max_rowpart = std::max<int32_t>(f->max_rowpart, (int32_t)rbs[i]);
+            f->max_colpart = std::max<int32_t>(f->max_colpart, (int32_t)cbs[i]);
+            f->max_n = std::max(f->max_n, f->nint[i]);
+            for (int c = 0; c < ncls; ++c) f->max_cnt[c] = std::max(f->max_cnt[c], f->cnt[(size_t)i * ncls + c]);
+            const int32_t *gc = &f->gcnt[(size_t)i * ncls * npc];
+            for (int g = 0; g < ncls * npc; ++g) f->max_gcnt[g] = std::max(f->max_gcnt[g], gc[g]);
         }
-        for (int g = 0; g < ncls * npc; ++g) {
-            const int cnt = t.gstart[g + 1] - t.gstart[g];
-            f->gcnt[(size_t)i * ncls * npc + g] = cnt;
-            f->max_gcnt[g] = std::max(f->max_gcnt[g], cnt);
-        }
-        std::copy(t.hist.begin(), t.hist.end(), f->hist.begin() + (size_t)i * t.hist.size());
     }
+    const double t3 = trace ? now() : 0.0;
     if (e == cudaSuccess && !tail_off) e = cudaStreamSynchronize(ctx->stream);   // the pinned staging buffer is reused
+    if (trace)
+        std::fprintf(stderr, "pk_forest_upload: %d trees, %.1f MB: layout %.0f us, pack + queue copies %.0f us, stats %.0f us, wait %.0f us\n",
+                     (int)(part_hi - part_lo), 1e-6 * (double)(offs[part_hi] - offs[part_lo]), 1e6 * (t1 - t0), 1e6 * (t2 - t1),
+                     1e6 * (t3 - t2), 1e6 * (now() - t3));
     if (e != cudaSuccess) {
         if (f->d_blocks) cudaFree(f->d_blocks);
         delete f;

@@ -83,10 +83,18 @@ class GramRunner(object):
 
         With W ranks each one packs and uploads 1/W of the trees and the ranks broadcast their byte ranges to each other
         device-to-device (NCCL over NVLink): the host packs the forest once per box instead of once per GPU."""
+        import os
+        import time
+        trace = bool(os.environ.get("PK_TRACE"))
+        t0 = time.perf_counter()
         if self.forest is not None:
             self.forest.close()
+        t1 = time.perf_counter()
         if self.world == 1:
             self.forest = Forest(self.ctx, self.flats, self.precision)
+            if trace:
+                print("GramRunner.upload: close %.0f us, Forest() %.0f us" % (1e6 * (t1 - t0), 1e6 * (time.perf_counter() - t1)),
+                      file=__import__("sys").stderr)
             return self.forest.nbytes()
         import torch.distributed as dist
         cuts = [self.n * r // self.world for r in range(self.world + 1)]

@@ -1,6 +1,7 @@
 """Turns one `ncu --set full` capture of the DP kernel into the two files under profiles/ that bench.py and the summary
-cite:  python scripts/ncu_extract.py gpurun_out/prof.ncu-rep <dps in the captured launch> <label> [file suffix]
-(developer tool; needs the `ncu` CLI, no GPU)."""
+cite:  python scripts/ncu_extract.py gpurun_out/prof.ncu-rep <dps in the captured launch> <label> <prefix> <tips> <precision>
+writes profiles/<prefix>_ncu_full_selected.csv, profiles/<prefix>_dram_traffic.json and (when the report carries source
+counters) profiles/<prefix>_stall_lines.csv  (developer tool; needs the `ncu` CLI, no GPU)."""
 import csv
 import io
 import json
@@ -24,11 +25,56 @@ KEEP = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_")
 
 
+def page(rep, which):
+    """CSV of one page of a report: from the .ncu-rep itself, or from <rep>.<page>.csv exported on the GPU box (the reports
+    are ~23 MB each with sources imported; scripts/profile_r02.sh exports the two pages there and drops the report)."""
+    if rep.endswith(".ncu-rep"):
+        return subprocess.run(["ncu", "-i", rep, "--page", which, "--csv"], capture_output=True, text=True).stdout
+    return open("%s.%s.csv" % (rep, which)).read()
+
+
+def stall_lines(rep, prefix, label, top=40):
+    """The SASS lines with the most warp-stall samples (source page of a capture taken with --import-source on)."""
+    raw = page(rep, "source")
+    rows = list(csv.reader(io.StringIO(raw)))
+    while rows and not (len(rows[0]) > 2 and rows[0][0].strip().lower() == "address"):      # "Kernel Name", ... line(s) first
+        rows.pop(0)
+    if len(rows) < 3:
+        return 0
+    hdr = rows[0]
+
+    def col(name):
+        for k, h in enumerate(hdr):
+            if h.strip().lower() == name:
+                return k
+        return -1
+    c_src, c_smp, c_exe, c_adr = col("source"), col("warp stall sampling (all samples)"), col("instructions executed"), col("address")
+    if c_src < 0 or c_smp < 0:
+        return 0
+    body = []
+    for r in rows[1:]:
+        try:
+            body.append((float(r[c_smp] or 0), r))
+        except (ValueError, IndexError):
+            continue
+    total = sum(b[0] for b in body) or 1.0
+    insts = sum(float(r[c_exe] or 0) for _, r in body if c_exe >= 0 and r[c_exe].replace(".", "").isdigit())
+    body.sort(key=lambda b: -b[0])
+    with open("profiles/%s_stall_lines.csv" % prefix, "w", newline="") as f:
+        f.write('"# ncu --set full --import-source on, source page (%s): the %d SASS lines with the most warp-stall samples; '
+                'total samples %d, warp instructions %d"\n' % (label.replace('"', "'"), top, total, insts))
+        w = csv.writer(f)
+        w.writerow(("offset", "samples_pct", "warp_instructions_executed", "sass"))
+        for smp, r in body[:top]:
+            w.writerow((r[c_adr] if c_adr >= 0 else "", "%.2f" % (100.0 * smp / total), r[c_exe] if c_exe >= 0 else "", r[c_src]))
+    return len(body)
+
+
 def main():
     rep, dps, label = sys.argv[1], int(sys.argv[2]), sys.argv[3]
-    suffix = sys.argv[4] if len(sys.argv) > 4 else ""          # e.g. "_fp32": a second capture next to the fp64 one
-    prec = 32 if "32" in suffix else 64
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    prefix = sys.argv[4]
+    tips, prec = int(sys.argv[5]), int(sys.argv[6])
+    raw = page(rep, "raw")
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, vals = rows[0], rows[1], rows[2]
     out = [("metric", "unit", "value")]
@@ -37,7 +83,7 @@ def main():
         if any(h == k or (k.endswith("_") and h.startswith(k) and "not_issued" not in h.lower()) for k in KEEP):
             out.append((h, u, v))
             got[h] = (u, v)
-    with open("profiles/r01_dp_kernel%s_ncu_full_selected.csv" % suffix, "w", newline="") as f:
+    with open("profiles/%s_ncu_full_selected.csv" % prefix, "w", newline="") as f:
         csv.writer(f).writerows(out)
 
     def to_bytes(name):
@@ -46,11 +92,13 @@ def main():
 
     rd, wr = to_bytes("dram__bytes_read.sum"), to_bytes("dram__bytes_write.sum")
     u, v = got["gpu__time_duration.sum"]
-    ms = float(v) * {"ms": 1, "us": 1e-3, "s": 1e3}[u]
+    ms = float(v.replace(",", "")) * {"ms": 1, "us": 1e-3, "s": 1e3, "ns": 1e-6}[u]
     json.dump({"command": label, "dps_in_launch": dps, "dram_bytes_read": rd, "dram_bytes_write": wr,
-               "kernel_ms_under_ncu": ms, "n_tips": 500, "precision": prec, "dram_bytes_per_dp": (rd + wr) / dps},
-              open("profiles/r01_dram_traffic%s.json" % suffix, "w"), indent=1)
-    print("wrote profiles/r01_dp_kernel%s_ncu_full_selected.csv (%d metrics) and profiles/r01_dram_traffic%s.json" % (suffix, len(out) - 1, suffix))
+               "kernel_ms_under_ncu": ms, "n_tips": tips, "precision": prec, "dram_bytes_per_dp": (rd + wr) / dps},
+              open("profiles/%s_dram_traffic.json" % prefix, "w"), indent=1)
+    n = stall_lines(rep, prefix, label)
+    print("wrote profiles/%s_ncu_full_selected.csv (%d metrics), profiles/%s_dram_traffic.json, stall lines from %d SASS lines"
+          % (prefix, len(out) - 1, prefix, n))
 
 
 if __name__ == "__main__":
