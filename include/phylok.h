@@ -119,12 +119,14 @@ int pk_ctx_sync(pk_ctx *ctx);
 /* tuning knobs (0 = default): threads per CTA (multiple of 32, >= widest class), CTAs per SM for the HBM-slab path,
  * C storage: 0 = automatic (shared memory only when it costs no resident CTAs), 1 = HBM slabs, 2 = shared memory */
 int pk_ctx_configure(pk_ctx *ctx, int32_t threads, int32_t ctas_per_sm, int32_t force_hbm);
-/* named test knobs: "unstaged" = 1 stages the tree parts in global memory even when they fit the shared memory of an SM
- * (the path trees beyond ~3 500 tips take by themselves) */
+/* named test / tuning knobs: "unstaged" = 1 stages both tree parts in global memory even when they fit the shared memory
+ * of an SM (the path trees beyond ~3 500 tips take by themselves), 2 = COLUMN part in global memory wherever possible (the
+ * path 1 600-3 000-tip trees take by themselves: two CTAs per SM instead of one), 3 = never, 0 = automatic */
 int pk_ctx_set_option(pk_ctx *ctx, const char *name, int32_t value);
 /* the most recent DP kernel launch on this ctx: ms = its device time (CUDA events recorded around that launch on the
  * ctx stream; blocks until it finished), launches = DP kernels launched since ctx creation, path = 0 (C in shared
- * memory) / 1 (C in HBM slabs) / 2 (HBM slabs, tree parts staged in global memory: trees beyond the shared-memory limit), launch_cfg = {grid, threads per CTA, dynamic shared memory bytes}. Any may be NULL. */
+ * memory) / 1 (C in HBM slabs) / 2 (HBM slabs, tree parts staged in global memory: trees beyond the shared-memory limit) / 3 (HBM slabs, ROW part
+ * in shared memory, COLUMN part in global memory), launch_cfg = {grid, threads per CTA, dynamic shared memory bytes}. Any may be NULL. */
 int pk_ctx_last_stats(pk_ctx *ctx, double *ms, int64_t *launches, int32_t *path, int32_t launch_cfg[3]);
 
 /* Results that came out non-finite since the last reset, counted by the DP kernel itself.  In fp32 mode a cell beyond

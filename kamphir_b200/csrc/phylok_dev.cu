@@ -388,6 +388,12 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
 #ifndef PK_UNROLL
 #define PK_UNROLL 4
 #endif
+#ifndef PK_DISCARD
+#define PK_DISCARD 0                // 1: discard a pair's stored cells from L2 when the pair is done (no write-back of dead cells)
+#endif
+#ifndef PK_COLGLOBAL_DEFAULT
+#define PK_COLGLOBAL_DEFAULT 0      // COLUMN part in the global staging area for the pairs that fit one CTA per SM otherwise
+#endif
 #ifndef PK_U2_BOUND
 #define PK_U2_BOUND 352
 #endif
@@ -403,10 +409,14 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
 // (pairs) being resident per SM.
 // DEAL: the 32-column chunks of all rectangles of a level are dealt to the warps (labelled trees: many narrow classes);
 // otherwise thread t owns column t of every rectangle and the rectangles of a level run one after the other.
-// STAGED = false: trees whose parts do not fit the shared memory of an SM.  The parts are copied into a per-CTA area in
-// global memory instead, patched there and read through L1 (uniform row records, once-per-rectangle column data): the
-// reference has no size limit (phyloK2.py:158-209), and neither has this path.
-template <typename T, bool CSMEM, int BOUND, bool DEAL, bool STAGED>     // BOUND: upper bound of the CTA size (sets the register budget)
+// STG: where a pair's tree parts are staged.
+//   1  ROW and COLUMN part in shared memory (TMA bulk copies): every tier up to ~1 600 tips at several CTAs per SM
+//   2  ROW part (and the row offsets) in shared memory, COLUMN part in a per-CTA area in global memory: a thread reads its
+//      column's node once per rectangle, so the column data need not be close; without them two CTAs of 1 600-3 000-tip
+//      pairs fit an SM where STG = 1 fits one (each thread then takes two or three columns of a rectangle in turn)
+//   0  both parts in the per-CTA global area, read through L1: trees beyond the shared-memory limit (~3 500 tips).  The
+//      reference has no size limit (phyloK2.py:158-209), and neither has this path.
+template <typename T, bool CSMEM, int BOUND, bool DEAL, int STG>     // BOUND: upper bound of the CTA size (sets the register budget)
 #ifndef PK_MINB192
 #define PK_MINB192 5
 #endif
@@ -423,7 +433,8 @@ template <typename T, bool CSMEM, int BOUND, bool DEAL, bool STAGED>     // BOUN
 // 80 registers) / 16 (fp32, 64 registers).  <= 192 threads: 5 CTAs of 64 registers (fp64 at 500 tips: 460 Gcells/s
 // against 452 for 4 CTAs of 80 registers, now that a cell takes 10 % fewer instructions; labelled fp64 stays at 4: its
 // chunk-dealing loop spills at 64 registers).
-__global__ void __launch_bounds__(BOUND, (BOUND <= 64    ? (sizeof(T) == 4 ? 16 : 12)
+__global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
+                                          : BOUND <= 64  ? (sizeof(T) == 4 ? 16 : 12)
                                           : BOUND <= 192 ? (sizeof(T) == 4 ? PK_MINB192_F32 : DEAL ? PK_MINB192_DEAL : PK_MINB192)
                                           : BOUND <= 224 ? 4 : BOUND <= 256 ? PK_MINB : BOUND <= 352 ? 3 : BOUND <= 384 ? 2 : BOUND <= 512 ? PK_MINB512
                                           : BOUND <= 576 ? 2 : 1))
@@ -440,6 +451,9 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 64    ? (sizeof(T) == 4 ? 16 
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ long long s_work[2];
+#if PK_DISCARD
+    __shared__ int s_used;
+#endif
     __shared__ int s_cntB[PK_MAX_CLASSES];
     __shared__ double s_part[32];
     __shared__ __align__(16) LevelDesc s_desc[PK_DESC_MAX];
@@ -448,11 +462,12 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 64    ? (sizeof(T) == 4 ? 16 
     int tid;                                                   // opaque read: lives in a register, never re-read via S2R
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
     const int lane = tid & 31, warp = tid >> 5;
-    unsigned char *const stage = STAGED ? smem : a.stage + (size_t)blockIdx.x * (size_t)a.stage_stride;
-    unsigned char *sA = stage;                                 // ROW part of the row tree (its records are patched in place)
-    unsigned char *sB = stage + a.tree_region;                 // COLUMN part of the column tree
-    const size_t info_at = (size_t)a.tree_region + a.col_region;
-    int *rowoff = reinterpret_cast<int *>(stage + info_at);
+    constexpr bool STAGED = STG != 0;                          // row records (and row offsets) in shared memory
+    unsigned char *const gstage = STG == 1 ? nullptr : a.stage + (size_t)blockIdx.x * (size_t)a.stage_stride;
+    unsigned char *sA = STAGED ? smem : gstage;                // ROW part of the row tree (its records are patched in place)
+    unsigned char *sB = STG == 1 ? smem + a.tree_region : STG == 2 ? gstage : gstage + a.tree_region;   // COLUMN part of the column tree
+    const size_t info_at = (size_t)a.tree_region + (STG == 2 ? 0 : a.col_region);
+    int *rowoff = reinterpret_cast<int *>((STAGED ? smem : gstage) + info_at);
     const unsigned long long slab_off = (unsigned long long)blockIdx.x * (unsigned long long)a.slab_elems;
     Cells<T, CSMEM> cells;
     cells.sm = reinterpret_cast<T *>(smem + info_at + a.rowinfo_bytes);
@@ -515,17 +530,21 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 64    ? (sizeof(T) == 4 ? 16 
             if (tid == 0) {
                 // the staging buffers were last written through the generic proxy (record patch, length scale, pad records)
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(&s_bar, bytesR + bytesC);
+                mbar_expect_tx(&s_bar, STG == 1 ? bytesR + bytesC : bytesR);
                 tma_bulk_g2s(sA, srcR, bytesR, &s_bar);
-                tma_bulk_g2s(sB, srcC, bytesC, &s_bar);
+                if (STG == 1) tma_bulk_g2s(sB, srcC, bytesC, &s_bar);
             }
-            mbar_wait(&s_bar, parity);
-            parity ^= 1;
         } else {
             // this CTA's private copies in global memory (the forest itself stays untouched: the records are patched per pair)
             for (uint32_t i = tid; i < bytesR / 16; i += NT) reinterpret_cast<int4 *>(sA)[i] = reinterpret_cast<const int4 *>(srcR)[i];
+        }
+        if (STG != 1) {
             for (uint32_t i = tid; i < bytesC / 16; i += NT) reinterpret_cast<int4 *>(sB)[i] = reinterpret_cast<const int4 *>(srcC)[i];
             __syncthreads();
+        }
+        if (STAGED) {
+            mbar_wait(&s_bar, parity);
+            parity ^= 1;
         }
         if (OVRQ && !CSMEM && tid < PK_PAD_RECORDS) {     // never-matching records after the last row (see PK_OVERRUN)
             int4 *padrec = reinterpret_cast<int4 *>(sA + bytesR) + 2 * tid;
@@ -578,6 +597,9 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 64    ? (sizeof(T) == 4 ? 16 
                 if (r < nA) rowoff[r] = carry + incl - len;
                 carry += __shfl_sync(0xffffffffu, incl, 31);
             }
+#if PK_DISCARD
+            if (lane == 0) s_used = carry;      // cells this pair stores
+#endif
         }
         __syncthreads();
         for (int r = tid; r < nA; r += NT) {      // patch the staged records with this pair's C offsets
@@ -705,6 +727,17 @@ __global__ void __launch_bounds__(BOUND, (BOUND <= 64    ? (sizeof(T) == 4 ? 16 
                 a.out[ia] = k;
             }
         }
+#if PK_DISCARD
+        // The stored cells of this pair are dead: every one of them has been read (at most once) by now.  Telling L2 so
+        // keeps them from being written back to HBM when the next pairs push them out (0.25 MB of DRAM writes per 500-tip
+        // pair otherwise, 88 % of the kernel's DRAM traffic).  A discard is a weak write: the barrier at the top of the loop
+        // orders it before the next pair's stores to the same lines.
+        if (!CSMEM) {
+            const int nlines = (int)(((long long)s_used * (long long)sizeof(T) + 127) >> 7);
+            for (int ln = tid; ln < nlines; ln += NT)
+                asm volatile("discard.global.L2 [%0], 128;" ::"l"(cells.base + ((unsigned long long)ln << 7)) : "memory");
+        }
+#endif
         // the next iteration's first __syncthreads orders these reads before the staging buffers are overwritten
     }
 }
@@ -740,7 +773,8 @@ struct pk_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     int cfg_threads = 0, cfg_ctas = 0, cfg_force_hbm = 0;
-    int opt_unstaged = 0;                       // 1: stage the tree parts in global memory even when they would fit (tests)
+    int opt_unstaged = 0;                       // 1: both tree parts in the global staging area even when they would fit (tests);
+                                                // 2: COLUMN part in the global area wherever possible, 3: never
     void *d_scratch = nullptr;
     size_t scratch_bytes = 0;
     unsigned long long *d_counters = nullptr;   // ring of work counters (one per launch in flight)
@@ -916,7 +950,10 @@ extern "C" int pk_ctx_configure(pk_ctx *ctx, int32_t threads, int32_t ctas_per_s
 extern "C" int pk_ctx_set_option(pk_ctx *ctx, const char *name, int32_t value) {
     if (!ctx || !name) return pk_fail(PK_ERR_INVALID, "null argument");
     const std::string key(name);
-    if (key == "unstaged") ctx->opt_unstaged = value ? 1 : 0;
+    if (key == "unstaged") {
+        if (value < 0 || value > 3) return pk_fail(PK_ERR_INVALID, "unstaged: 0 (automatic), 1 (both parts global), 2 (column part global), 3 (never)");
+        ctx->opt_unstaged = value;
+    }
     else return pk_fail(PK_ERR_INVALID, "unknown option '" + key + "'");
     return PK_OK;
 }
@@ -1236,7 +1273,7 @@ extern "C" int pk_forest_pair_stats(const pk_forest *fa, const pk_forest *fb, co
 // ---------------------------------------------------------------------------------------------------
 // The dynamic shared-memory limit of a kernel variant is raised once per size and its occupancy is queried once per
 // (CTA size, shared memory): a sim-vs-obs proposal is one 30 us launch, the driver calls would cost more than that.
-template <typename T, bool CSMEM, int BOUND, bool DEAL, bool STAGED>
+template <typename T, bool CSMEM, int BOUND, bool DEAL, int STAGED>
 static cudaError_t launch_t(pk_ctx *ctx, const DpArgs &args, int grid, int nt, int smem, cudaStream_t stream) {
     int &have = ctx->attr_smem[{(int)sizeof(T) + 16 * (int)DEAL + 32 * (int)STAGED, (int)CSMEM, BOUND}];
     if (smem > have) {
@@ -1249,7 +1286,7 @@ static cudaError_t launch_t(pk_ctx *ctx, const DpArgs &args, int grid, int nt, i
     return cudaGetLastError();
 }
 
-template <typename T, bool CSMEM, int BOUND, bool DEAL, bool STAGED>
+template <typename T, bool CSMEM, int BOUND, bool DEAL, int STAGED>
 static cudaError_t occupancy_t(pk_ctx *ctx, int nt, int smem, int *blocks) {
     auto key = std::make_tuple((int)sizeof(T) + 16 * (int)DEAL + 32 * (int)STAGED, (int)CSMEM, BOUND, nt, smem);
     auto it = ctx->occupancy.find(key);
@@ -1274,22 +1311,24 @@ static cudaError_t occupancy_t(pk_ctx *ctx, int nt, int smem, int *blocks) {
 // <= 384: 80 (2 CTAs), <= 576: 56 (2 CTAs; 1500 tips: 432 against 378 with one CTA), <= 512: 64 (2 CTAs; one CTA of 128 registers ran 5 %
 // (fp64) / 37 % (fp32) slower at 1300 tips), <= 768: 80, else 64 (one CTA per SM)
 #define PK_DISPATCH_NT(FN, TT, CS, DL, ...)                                                     \
-    (nt <= 64    ? FN<TT, CS, 64, DL, true>(__VA_ARGS__)                                              \
-     : nt <= 192 ? FN<TT, CS, 192, DL, true>(__VA_ARGS__)                                           \
-     : nt <= 224 ? FN<TT, CS, 224, DL, true>(__VA_ARGS__)                                             \
-     : nt <= 256 ? FN<TT, CS, 256, DL, true>(__VA_ARGS__)                                             \
-     : nt <= 320 ? FN<TT, CS, 320, DL, true>(__VA_ARGS__)                                             \
-     : nt <= 352 ? FN<TT, CS, 352, DL, true>(__VA_ARGS__)                                             \
-     : nt <= 384 ? FN<TT, CS, 384, DL, true>(__VA_ARGS__)                                             \
-     : nt <= 512 ? FN<TT, CS, 512, DL, true>(__VA_ARGS__)                                             \
-     : nt <= 576 ? FN<TT, CS, 576, DL, true>(__VA_ARGS__)                                             \
-     : nt <= 768 ? FN<TT, CS, 768, DL, true>(__VA_ARGS__)                                             \
-                 : FN<TT, CS, 1024, DL, true>(__VA_ARGS__))
+    (nt <= 64    ? FN<TT, CS, 64, DL, 1>(__VA_ARGS__)                                              \
+     : nt <= 192 ? FN<TT, CS, 192, DL, 1>(__VA_ARGS__)                                           \
+     : nt <= 224 ? FN<TT, CS, 224, DL, 1>(__VA_ARGS__)                                             \
+     : nt <= 256 ? FN<TT, CS, 256, DL, 1>(__VA_ARGS__)                                             \
+     : nt <= 320 ? FN<TT, CS, 320, DL, 1>(__VA_ARGS__)                                             \
+     : nt <= 352 ? FN<TT, CS, 352, DL, 1>(__VA_ARGS__)                                             \
+     : nt <= 384 ? FN<TT, CS, 384, DL, 1>(__VA_ARGS__)                                             \
+     : nt <= 512 ? FN<TT, CS, 512, DL, 1>(__VA_ARGS__)                                             \
+     : nt <= 576 ? FN<TT, CS, 576, DL, 1>(__VA_ARGS__)                                             \
+     : nt <= 768 ? FN<TT, CS, 768, DL, 1>(__VA_ARGS__)                                             \
+                 : FN<TT, CS, 1024, DL, 1>(__VA_ARGS__))
 // unstaged: trees beyond the shared-memory staging limit (parts in a per-CTA global area, C in HBM slabs, 1024-thread tier)
+// (colglobal: 1 600-3 000-tip trees, COLUMN part in the per-CTA global area, <= 384 threads taking several columns each)
 #define PK_DISPATCH_CS(FN, TT, DL, ...)                          \
-    (unstaged ? FN<TT, false, 1024, DL, false>(__VA_ARGS__)      \
-     : csmem  ? PK_DISPATCH_NT(FN, TT, true, DL, __VA_ARGS__)    \
-              : PK_DISPATCH_NT(FN, TT, false, DL, __VA_ARGS__))
+    (stg == 0   ? FN<TT, false, 1024, DL, 0>(__VA_ARGS__)        \
+     : stg == 2 ? FN<TT, false, 384, false, 2>(__VA_ARGS__)      \
+     : csmem    ? PK_DISPATCH_NT(FN, TT, true, DL, __VA_ARGS__)  \
+                : PK_DISPATCH_NT(FN, TT, false, DL, __VA_ARGS__))
 #define PK_DISPATCH(FN, ...)                                                                                \
     (prec32 ? (deal ? PK_DISPATCH_CS(FN, float, true, __VA_ARGS__) : PK_DISPATCH_CS(FN, float, false, __VA_ARGS__)) \
             : (deal ? PK_DISPATCH_CS(FN, double, true, __VA_ARGS__) : PK_DISPATCH_CS(FN, double, false, __VA_ARGS__)))
@@ -1366,7 +1405,7 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
     const long long base_smem = (long long)region_r + region_c + rowinfo;
     const long long limit = ctx->smem_optin - 16384;   // static shared memory (table, level descriptors, ...)
     // trees too large to stage in shared memory (~3 500 tips): their parts are staged in a per-CTA area in global memory
-    const bool unstaged = base_smem > limit || ctx->opt_unstaged;
+    int stg = (base_smem > limit || ctx->opt_unstaged == 1) ? 0 : 1;
     const long long c_bytes = ((maxM * (long long)w) + 127) & ~127ll;
     args.tree_region = region_r;
     args.col_region = region_c;
@@ -1392,9 +1431,34 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
     // C in shared memory only when that costs no resident CTAs: with C in a global slab the CTAs of small pairs stay
     // L2-resident anyway and more pairs per SM hide the level barriers better (measured: profiles/r01_summary.md)
     bool csmem = false;
-    int smem = unstaged ? 0 : (int)base_smem, per_sm = 0;
+    int smem = stg == 0 ? 0 : (int)base_smem, per_sm = 0;
     cudaError_t e = PK_DISPATCH(occupancy_t, ctx, nt, smem, &per_sm);
-    if (e == cudaSuccess && !unstaged && ctx->cfg_force_hbm != 1 && base_smem + c_bytes <= limit) {
+    // Big pairs (1 600 tips and more) fit one CTA per SM with both parts in shared memory.  With the COLUMN part in the
+    // per-CTA global area two CTAs fit, each with half (a third, ...) as many threads, every thread taking that many
+    // columns of a rectangle in turn: two independent pairs per SM overlap each other's level barriers and gather
+    // latencies (opt_unstaged: 2 = wherever possible, 3 = never).
+    if (e == cudaSuccess && stg == 1 && !deal && ctx->opt_unstaged != 3 && !ctx->cfg_threads &&
+        (ctx->opt_unstaged == 2 || (per_sm == 1 && PK_COLGLOBAL_DEFAULT))) {
+        int passes = 1;
+        while (((((typ_w + passes - 1) / passes) + 31) & ~31) > 384) ++passes;
+        if (ctx->opt_unstaged != 2 && passes == 1) passes = 2;
+        const int nt2 = std::max(64, (((typ_w + passes - 1) / passes) + 31) & ~31);
+        const int smem2 = region_r + rowinfo;
+        int occ2 = 0;
+        const int keep = stg;
+        stg = 2;
+        const int nt_keep = nt;
+        nt = nt2;
+        e = PK_DISPATCH(occupancy_t, ctx, nt, smem2, &occ2);
+        if (e == cudaSuccess && smem2 <= limit && (occ2 >= 2 || ctx->opt_unstaged == 2) && occ2 >= 1) {
+            smem = smem2;
+            per_sm = occ2;
+        } else {
+            stg = keep;
+            nt = nt_keep;
+        }
+    }
+    if (e == cudaSuccess && stg == 1 && ctx->cfg_force_hbm != 1 && base_smem + c_bytes <= limit) {
         int occ_smem = 0;
         csmem = true;
         e = PK_DISPATCH(occupancy_t, ctx, nt, (int)(base_smem + c_bytes), &occ_smem);
@@ -1417,7 +1481,7 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
         args.slab_elems = ((((maxM + slack) * (long long)w) + 255) & ~255ll) / (long long)w;
         // the slabs, then (unstaged) one staging area per CTA
         const size_t slab_bytes = ((size_t)grid * (size_t)args.slab_elems * w + 255) & ~(size_t)255;
-        args.stage_stride = unstaged ? (long long)((base_smem + 255) & ~255ll) : 0;
+        args.stage_stride = stg == 0 ? (long long)((base_smem + 255) & ~255ll) : stg == 2 ? (long long)((region_c + 255) & ~255) : 0;
         int rc = ensure_scratch(ctx, slab_bytes + (size_t)grid * (size_t)args.stage_stride);
         if (rc) return rc;
         args.scratch = ctx->d_scratch;
@@ -1446,7 +1510,7 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
 #endif
     ctx->ev_valid = true;
     ctx->launches++;
-    ctx->last_path = csmem ? 0 : (unstaged ? 2 : 1);
+    ctx->last_path = csmem ? 0 : (stg == 0 ? 2 : stg == 2 ? 3 : 1);
     ctx->last_grid = grid;
     ctx->last_threads = nt;
     ctx->last_smem = smem;

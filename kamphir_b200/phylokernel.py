@@ -219,7 +219,7 @@ class Context(object):
         cfg = (ctypes.c_int32 * 3)()
         check(_lib.lib().pk_ctx_last_stats(self._h, ctypes.byref(ms), ctypes.byref(launches), ctypes.byref(path), cfg))
         return dict(ms=ms.value, launches=launches.value,
-                    path={0: "smem", 1: "hbm", 2: "hbm-unstaged"}.get(path.value, "hbm"),
+                    path={0: "smem", 1: "hbm", 2: "hbm-unstaged", 3: "hbm-colglobal"}.get(path.value, "hbm"),
                     grid=cfg[0], threads=cfg[1], smem_bytes=cfg[2])
 
     def nonfinite(self, reset=True):
