@@ -13,6 +13,7 @@
 #include <atomic>
 #include <charconv>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <condition_variable>
@@ -96,7 +97,24 @@ std::mutex g_pool_make;
 std::once_flag g_atfork_once;
 }  // namespace
 
-int pk_host_threads() { return (int)std::max(1u, std::thread::hardware_concurrency()); }
+// Host threads this process may use: the hardware concurrency, divided by the number of ranks that share the host when
+// a launcher says so (torchrun sets LOCAL_WORLD_SIZE: 8 ranks each packing their part of a forest on 32 threads of a
+// 32-core host only get in each other's way); PK_HOST_THREADS overrides.
+int pk_host_threads() {
+    static const int n = []() {
+        int hc = (int)std::max(1u, std::thread::hardware_concurrency());
+        if (const char *e = std::getenv("PK_HOST_THREADS")) {
+            const int v = std::atoi(e);
+            if (v > 0) return v;
+        }
+        if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) {
+            const int v = std::atoi(e);
+            if (v > 1) hc = std::max(1, hc / v);
+        }
+        return hc;
+    }();
+    return n;
+}
 
 void pk_parallel(int workers, const std::function<void(int)> &fn) {
     if (workers <= 1) {

@@ -1,5 +1,6 @@
 // Internal definitions shared by the host flattener (phylok_host.cpp) and the device side (phylok_dev.cu).
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cstddef>
 #include <functional>
@@ -11,6 +12,11 @@
 
 #define PK_MAX_CLASSES 64          // 1 + 2S + S*S production classes with S <= 7 tip states
 #define PK_HDR_INTS 16             // per-tree block header, 64 bytes
+
+inline uint64_t pk_next_tree_uid() {
+    static std::atomic<uint64_t> next{1};
+    return next.fetch_add(1);
+}
 
 // ---- one flattened tree (host) ---------------------------------------------------------------------
 // Post-order arrays are exactly what annotate_tree (phyloK2.py:132-146) hangs on the Clade objects.
@@ -46,6 +52,7 @@ struct pk_tree {
     std::vector<int32_t> colorder;  // [n]   column -> post-order index
     std::vector<int32_t> krank;     // [n]   post-order index -> rank within its (class, parent code) group
     std::vector<int32_t> gstart;    // [ncls * npc + 1]  first column of group (class, parent code); npc = 2 * ncls + 2
+    uint64_t uid = pk_next_tree_uid();   // never reused: identifies the tree in the per-context cache of packed tree sets
 };
 
 // Device block of one tree: two independently staged parts, both 16-byte aligned.

@@ -40,6 +40,7 @@ class GramRunner(object):
         self.ctx = get_context(device)
         self.L = _lib.lib()
         self.forest = None
+        self._handles = Forest.handle_array(self.flats)
         self.d_out = ctypes.c_void_p()        # where this rank's kernel writes (local or rank 0's mapped buffer)
         self.d_local = ctypes.c_void_p()      # buffer this rank owns (rank 0 always; all ranks for allreduce)
         self.d_diag = ctypes.c_void_p()
@@ -91,15 +92,19 @@ class GramRunner(object):
             self.forest.close()
         t1 = time.perf_counter()
         if self.world == 1:
-            self.forest = Forest(self.ctx, self.flats, self.precision)
+            self.forest = Forest(self.ctx, self.flats, self.precision, keep=False, handles=self._handles)
             if trace:
                 print("GramRunner.upload: close %.0f us, Forest() %.0f us" % (1e6 * (t1 - t0), 1e6 * (time.perf_counter() - t1)),
                       file=__import__("sys").stderr)
             return self.forest.nbytes()
+        import torch
         import torch.distributed as dist
         cuts = [self.n * r // self.world for r in range(self.world + 1)]
-        self.forest = Forest(self.ctx, self.flats, self.precision, part=(cuts[self.rank], cuts[self.rank + 1]))
+        self.forest = Forest(self.ctx, self.flats, self.precision, part=(cuts[self.rank], cuts[self.rank + 1]), keep=False,
+                             handles=self._handles)
+        t2 = time.perf_counter()
         self.ctx.sync()
+        t3 = time.perf_counter()
         mine = 0
         for r in range(self.world):
             ptr, nbytes = self.forest.device_range(cuts[r], cuts[r + 1])
@@ -107,8 +112,12 @@ class GramRunner(object):
                 mine = nbytes
             if nbytes:
                 dist.broadcast(_as_tensor(ptr, nbytes, "|u1"), src=self._global_rank(r), group=self.group)
-        import torch
+        t4 = time.perf_counter()
         torch.cuda.current_stream().synchronize()
+        if trace and self.rank == 0:
+            print("GramRunner.upload: close %.0f us, Forest(part) %.0f us, sync %.0f us, %d broadcasts queued %.0f us, "
+                  "waited %.0f us" % (1e6 * (t1 - t0), 1e6 * (t2 - t1), 1e6 * (t3 - t2), self.world, 1e6 * (t4 - t3),
+                                      1e6 * (time.perf_counter() - t4)), file=__import__("sys").stderr)
         return mine + 32 * self.n           # + the meta records every rank uploads
 
     # -- one step ---------------------------------------------------------------------------------------

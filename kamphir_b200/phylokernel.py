@@ -243,16 +243,17 @@ class Context(object):
 class Forest(object):
     """Device-resident packed SoA of a set of FlatTrees (``pk_forest*``)."""
 
-    def __init__(self, ctx, trees, precision=64, part=None, keep=True):
+    def __init__(self, ctx, trees, precision=64, part=None, keep=True, handles=None):
         """part=(lo, hi): pack and upload only those trees (the rest of the device forest is filled by the other ranks,
         see GramRunner.upload); the layout and the statistics always cover the whole set.  keep=False: do not hold on
-        to the FlatTrees (the device copy does not need them once it is made)."""
+        to the FlatTrees (the device copy does not need them once it is made).  handles: the ctypes array of the trees'
+        handles when the caller uploads the same list again and again (building it costs 0.6 ms for 4096 trees)."""
         self.ctx = ctx
-        trees = list(trees)
+        trees = list(trees) if handles is None or keep else trees
         self.trees = trees if keep else None
         self.n = len(trees)
         self.precision = int(precision)
-        arr = (ctypes.c_void_p * self.n)(*[t._h for t in trees])
+        arr = handles if handles is not None else Forest.handle_array(trees)
         out = ctypes.c_void_p()
         if part is None:
             check(_lib.lib().pk_forest_upload(ctx._h, arr, self.n, self.precision, ctypes.byref(out)))
@@ -260,6 +261,10 @@ class Forest(object):
             check(_lib.lib().pk_forest_upload_part(ctx._h, arr, self.n, self.precision, int(part[0]), int(part[1]),
                                                    ctypes.byref(out)))
         self._h = out
+
+    @staticmethod
+    def handle_array(trees):
+        return (ctypes.c_void_p * len(trees))(*[t._h for t in trees])
 
     def device_range(self, lo, hi):
         """(device pointer, bytes) of the packed blocks of trees [lo, hi)."""

@@ -284,3 +284,41 @@ def test_5000_tip_pair_beyond_the_staging_limit(precision):
     assert rel(got, want) <= TOL[precision]
     res = pk.score_batch(a, [b, c])
     assert abs(res["knorm"][0] - want[0] / math.sqrt(want[1] * c_oracle.kernel(ob, ob, 0.2, 2.0))) <= 10 * TOL[precision]
+
+
+def test_repeated_uploads_of_a_tree_set_come_out_of_the_cached_image():
+    """A set of >= 64 trees uploaded a second time in a row is kept as a page-locked packed image; later uploads are one
+    copy out of it.  Same matrix every time, also when two sets alternate and when only part of the set is uploaded."""
+    from kamphir_b200.gram import GramRunner
+    sets = [synth.tree_set(70, 45, 9800, "mixed"), synth.tree_set(66, 60, 9900, "mixed")]
+    flats = [[FlatTree.from_newick(s) for s in nwk] for nwk in sets]
+    pk = PhyloKernel(**KAM)
+    want = [pk.gram(f, normalised=True) for f in flats]
+    runners = [GramRunner(f, 0.2, 2.0, 1.0, 64, True, 8) for f in flats]
+    for order in ((0, 0, 0, 0), (1, 1, 1), (0, 1, 0, 1), (1, 1, 0, 0, 0)):
+        for k in order:
+            r = runners[k]
+            r.upload()
+            r.zero()
+            r.launch()
+            r.finish()
+            assert np.array_equal(r.fetch(copy=True), want[k])
+    # a part upload (what a rank of a multi-GPU run does) next to the plain one of the same trees
+    ctx = get_context()
+    for rep in range(3):
+        part = Forest(ctx, flats[0], 64, part=(10, 40))
+        full = Forest(ctx, flats[0], 64)
+        lo, hi = 10, 40
+        pa, na = part.device_range(lo, hi)
+        pb, nb = full.device_range(lo, hi)
+        assert na == nb and na > 0
+        a, b = np.empty(na, np.uint8), np.empty(nb, np.uint8)
+        from kamphir_b200 import _lib
+        from kamphir_b200._lib import check
+        check(_lib.lib().pk_memcpy_d2h(ctx._h, a.ctypes.data, pa, na))
+        check(_lib.lib().pk_memcpy_d2h(ctx._h, b.ctypes.data, pb, nb))
+        assert np.array_equal(a, b)
+        part.close()
+        full.close()
+    for r in runners:
+        r.close()
