@@ -48,7 +48,12 @@ def main():
         prec = int(rng.choice([64, 64, 32]))
         threads = int(rng.choice([0, 0, 64, 128, 256]))
         storage = int(rng.choice([0, 0, 1, 2])) if not big else 0
+        # where the tree parts are staged: automatic, both parts in global memory, COLUMN part in global memory (unlabelled)
+        stage = int(rng.choice([0, 0, 1, 2]))
+        if stage == 2 and (S or threads):
+            stage = 1
         get_context().configure(threads, 0, storage)
+        get_context().set_option("unstaged", stage)
         flats = [FlatTree.from_newick(s, 3, norm, S) for s in nwk]
         pairs = [(int(a), int(b)) for a, b in rng.integers(0, ntrees, size=(12, 2))] + [(0, 0)]
         pk = PhyloKernel(decayFactor=lam, gaussFactor=tau, sigma=sig, precision=prec, n_states=S, normalize=norm)
@@ -66,7 +71,7 @@ def main():
             want = [c_oracle.kernel(of[a], of[b], lam, tau, sig) for a, b in pairs]
         got, want = np.asarray(got), np.asarray(want)
         # cells overflow beyond 3e38 in fp32 (1.8e308 in fp64, in the oracle too) with decayFactor near 1 on deep, similar trees
-        keep = want < (1e30 if prec == 32 else 1e300)
+        keep = want < 1e300      # fp32 overflow (beyond 3e38) is re-evaluated in fp64 by the library itself
         got, want = got[keep], want[keep]
         if not len(want):
             continue
@@ -77,11 +82,14 @@ def main():
         worst[prec] = max(worst[prec], err)
         checked += len(pairs)
         tol = 1e-9 if prec == 64 else 1e-5
+        if prec == 32 and np.any(want > 1e30):      # near the fp32 range the cells lose their last bits before they overflow
+            tol = 1e-4
         if err > tol:
-            print("MISMATCH round %d: S=%d norm=%s lam=%g tau=%g sig=%g prec=%d threads=%d storage=%d err=%.3g sizes=%s"
-                  % (rd, S, norm, lam, tau, sig, prec, threads, storage, err, [f.n_internal + 1 for f in flats]))
+            print("MISMATCH round %d: S=%d norm=%s lam=%g tau=%g sig=%g prec=%d threads=%d storage=%d stage=%d err=%.3g sizes=%s"
+                  % (rd, S, norm, lam, tau, sig, prec, threads, storage, stage, err, [f.n_internal + 1 for f in flats]))
             sys.exit(1)
     get_context().configure(0, 0, 0)
+    get_context().set_option("unstaged", 0)
     print("fuzz ok: %d rounds, %d pairs, worst relative error fp64 %.3g fp32 %.3g, %.1f s"
           % (rounds, checked, worst[64], worst[32], time.time() - t0))
 

@@ -14,6 +14,12 @@ for prec in (64, 32):
         k = pk.kernel_batch(flats[:9])
         assert np.all(np.isfinite(k))
     get_context().configure(0, 0, 0)
+    for stage in (1, 2):      # tree parts staged in global memory: both, COLUMN part only
+        get_context().set_option("unstaged", stage)
+        k = pk.kernel_batch(flats[:9])
+        assert np.all(np.isfinite(k))
+        assert np.all(np.isfinite(pk.gram(flats[3:], normalised=False)))
+    get_context().set_option("unstaged", 0)
     g = pk.gram(flats, normalised=True)
     assert np.allclose(np.diag(g), 1.0)
     r = pk.score_batch(flats[6], flats[:6])
