@@ -1547,6 +1547,25 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
         if (PK_OVERRUN)
             for (size_t g = 0; g < fa->max_gcnt.size(); ++g) slack = std::max<long long>(slack, std::max(fa->max_gcnt[g], fb->max_gcnt[g]));
         args.slab_elems = ((((maxM + slack) * (long long)w) + 255) & ~255ll) / (long long)w;
+        if (args.slab_elems >= (1ll << 31))
+            return pk_fail(PK_ERR_INVALID, "tree pair too large: " + std::to_string(args.slab_elems) + " stored cells exceed the 32-bit cell index");
+        // Every resident CTA owns one slab.  Huge pairs (tens of thousands of tips: hundreds of MB per slab) run on fewer
+        // CTAs rather than asking for more memory than the device has.
+        {
+            const size_t per_cta = (size_t)args.slab_elems * w + (stg == 0 ? (size_t)base_smem + 256 : stg == 2 ? (size_t)region_c + 256 : 0);
+            if ((size_t)grid * per_cta > ctx->scratch_bytes) {
+                size_t free_b = 0, total_b = 0;
+                if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                    const size_t budget = (size_t)(0.8 * (double)(free_b + ctx->scratch_bytes));
+                    const long long fit = (long long)(budget / per_cta);
+                    if (fit < 1)
+                        return pk_fail(PK_ERR_NOMEM, "tree pair too large: one C slab of " + std::to_string(per_cta >> 20) + " MB does not fit the device memory");
+                    grid = (int)std::min<long long>(grid, fit);
+                } else {
+                    cudaGetLastError();
+                }
+            }
+        }
         // the slabs, then (unstaged) one staging area per CTA
         const size_t slab_bytes = ((size_t)grid * (size_t)args.slab_elems * w + 255) & ~(size_t)255;
         args.stage_stride = stg == 0 ? (long long)((base_smem + 255) & ~255ll) : stg == 2 ? (long long)((region_c + 255) & ~255) : 0;
