@@ -184,8 +184,8 @@ __device__ __forceinline__ int pk_div(int a, int b) { return __float2int_rz(__fd
 template <typename T>
 struct __align__(16) RowRec {
     T a0, a1;
-    char pad[16 - 2 * sizeof(T)];
-    int off0, off1, st_off, packed;     // bytes 16..31: read as one int4
+    int st2, pk2;                       // fp32, PK_PACKQ: copies of st_off / packed, so one LDS.128 brings the lengths and what the store needs
+    int off0, off1, st_off, packed;     // bytes 16..31: read as one int4 (PK_PACKQ: the first 8 bytes, with the child classes in the top bytes)
 };
 template <>
 struct __align__(16) RowRec<double> {
@@ -291,19 +291,46 @@ __device__ __forceinline__ int4 ld_int4(const int4 *p) {
 #define PK_FENCE_ALL 0
 #endif
 #define PK_PAD_RECORDS 4      // >= the largest U
+// PK_PACKQ: the class of a row's child (+ 1, 0 = tip) rides in the top byte of the child's stored-row offset, so the
+// prefetch of a row needs 8 bytes of its record instead of 16 (one shared-memory wavefront instead of two per row and
+// warp; the LSU data pipe is the busiest unit of the kernel).  The column keeps the same byte in the top byte of its test
+// word and its rank pre-biased by minus that byte, so "offset word + biased rank" is the cell index without any masking.
+// Needs offsets below 2^24 (pairs up to ~10 000 tips); bigger slabs take the plain records.
+#ifndef PK_PACKQ
+#define PK_PACKQ 1
+#endif
+template <bool STAGED>
+__device__ __forceinline__ int2 ld_int2(const int2 *p) {
+    int2 v;
+    if (STAGED) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_u32(p)));
+    else asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
 // child cell of slot 0 / 1: the stored cell when the children's classes agree, else cell 1 (= 1, productions differ)
-#define PK_GATHER0(q) C.ld((((q).w ^ qb0) & 0xff) == 0 ? (q).x + kb0 : 1)
-#define PK_GATHER1(q) C.ld((((q).w ^ qb1) & 0xff00) == 0 ? (q).y + kb1 : 1)
-template <typename T, bool CSMEM, bool STAGED, bool G0, bool G1, int U, bool FENCE, bool OVRQ>
+#define PK_GATHER0(q) (PQ ? C.ld((((q).x ^ qb0) & 0xff000000) == 0 ? (q).x + kb0 : 1) : C.ld((((q).w ^ qb0) & 0xff) == 0 ? (q).x + kb0 : 1))
+#define PK_GATHER1(q) (PQ ? C.ld((((q).y ^ qb1) & 0xff000000) == 0 ? (q).y + kb1 : 1) : C.ld((((q).w ^ qb1) & 0xff00) == 0 ? (q).y + kb1 : 1))
+// the part of a row record the gathers need: PQ: {offset | class << 24} of both children (8 bytes), else the whole second half
+#define PK_LOADQ(ptr)                                                                                   \
+    int4 q;                                                                                             \
+    if (PQ) {                                                                                           \
+        const int2 q2 = ld_int2<STAGED>(reinterpret_cast<const int2 *>(ptr));                           \
+        q = make_int4(q2.x, q2.y, 0, 0);                                                                \
+    } else {                                                                                            \
+        q = ld_int4<STAGED>(ptr);                                                                       \
+    }
+template <typename T, bool CSMEM, bool STAGED, bool G0, bool G1, int U, bool FENCE, bool OVRQ, bool PQ>
 __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0, T b1, int cb0, int cb1, int pkey,
                                      const Cells<T, CSMEM> &C, const GaussK<T> &gk, T sigma, T tipf) {
     constexpr bool OVR = OVRQ && !CSMEM;         // the prefetch may run past the rectangle (see PK_OVERRUN)
-    int qb0 = (unsigned)cb0 >> 24;                                         // child class + 1 (0 = tip)
+    // child class + 1 (0 = tip) where the row record has it: top byte of the offset word (PQ) or byte 0 / 1 of rec.packed
+    int qb0 = PQ ? (int)((unsigned)cb0 & 0xff000000u) : (int)((unsigned)cb0 >> 24);
 #if PK_OPAQUE_Q
     asm("" : "+r"(qb0));      // hide the value range: the class test of slot 0 stays one LOP3 with a predicate result
 #endif
-    const int kb0 = cb0 & 0xffffff;                                        // rank in its group
-    const int qb1 = ((unsigned)cb1 >> 24) << 8, kb1 = cb1 & 0xffffff;      // ... aligned with byte 1 of rec.packed
+    const int qb1 = PQ ? (int)((unsigned)cb1 & 0xff000000u) : (int)(((unsigned)cb1 >> 24) << 8);
+    // rank in its group; PQ: minus the class byte, so that offset word + rank is the cell index
+    const int kb0 = PQ ? (cb0 & 0xffffff) - (int)((unsigned)cb0 & 0xff000000u) : (cb0 & 0xffffff);
+    const int kb1 = PQ ? (cb1 & 0xffffff) - (int)((unsigned)cb1 & 0xff000000u) : (cb1 & 0xffffff);
     T cf = (T)1;                                                           // factor of the slots that are tips in every row
     if (!G0) cf = qb0 == 0 ? tipf : (T)1;
     if (!G1) cf *= qb1 == 0 ? tipf : (T)1;
@@ -314,16 +341,28 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
     if ((G0 || G1) && U <= rows) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int4 q = ld_int4<STAGED>(ip + 2 * u + 1);
+            PK_LOADQ(ip + 2 * u + 1)
             if (G0) f0[u] = PK_GATHER0(q);
             if (G1) f1[u] = PK_GATHER1(q);
         }
     }
     for (; rr + U <= rows; rr += U, rp += U, ip += 2 * U) {
         T x[U], ev[U], g[U];
+        int so[U], pk[U];      // fp32 + PQ: the store offset and packed word arrive with the lengths
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const T d0 = rp[u].a0 - b0, d1 = rp[u].a1 - b1;
+            T a0, a1;
+            if (PQ && sizeof(T) == 4) {
+                const int4 h = ld_int4<STAGED>(ip + 2 * u);
+                a0 = (T)__int_as_float(h.x);
+                a1 = (T)__int_as_float(h.y);
+                so[u] = h.z;
+                pk[u] = h.w;
+            } else {
+                a0 = rp[u].a0;
+                a1 = rp[u].a1;
+            }
+            const T d0 = a0 - b0, d1 = a1 - b1;
             x[u] = fma(d1, d1, d0 * d0);
             g[u] = G0 ? (G1 ? f0[u] * f1[u] : f0[u] * cf) : (G1 ? f1[u] * cf : cf);
         }
@@ -331,7 +370,7 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
             const int4 *np = OVR || rr + 2 * U <= rows ? ip + 2 * U : ip;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int4 q = ld_int4<STAGED>(np + 2 * u + 1);
+                PK_LOADQ(np + 2 * u + 1)
                 if (G0) f0[u] = PK_GATHER0(q);
                 if (G1) f1[u] = PK_GATHER1(q);
             }
@@ -349,7 +388,11 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
         pk_gauss<U>(x, ev, gk);
 #pragma unroll
         for (int u = 0; u < U; ++u) {     // e * g feeds two FMAs: the stored cell sigma + C and the running sum
-            if (((rp[u].packed ^ pkey) & 0xff0000) == 0) C.st(rp[u].st_off + jb, fma(ev[u], g[u], sigma));
+            if (!(PQ && sizeof(T) == 4)) {
+                pk[u] = rp[u].packed;
+                so[u] = rp[u].st_off;
+            }
+            if (((pk[u] ^ pkey) & 0xff0000) == 0) C.st(so[u] + jb, fma(ev[u], g[u], sigma));
             part = fma(ev[u], g[u], part);
         }
     }
@@ -361,7 +404,7 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
 #pragma unroll
             for (int u = 0; u < U - 1; ++u) {
                 if (u < rem) {
-                    const int4 q = ld_int4<STAGED>(ip + 2 * u + 1);
+                    PK_LOADQ(ip + 2 * u + 1)
                     if (G0) f0[u] = PK_GATHER0(q);
                     if (G1) f1[u] = PK_GATHER1(q);
                 }
@@ -463,6 +506,11 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
     const int lane = tid & 31, warp = tid >> 5;
     constexpr bool STAGED = STG != 0;                          // row records (and row offsets) in shared memory
+    // child classes packed into the offset words (offsets < 2^24): where it measured faster -- fp64, unlabelled, the
+    // 192-thread tier (200-550 tips: 468 against 460 Gcells/s at 500 tips, 348 against 342 at 200), the 320-thread tier
+    // (800 tips: 442 against 425) and the 384-thread one (1000 tips: 434 against 432).  fp32 (788 against 805 at 500 tips),
+    // the 64-thread tier, the big CTAs (2000 tips: 422 against 437) and the labelled variant lose with it.
+    constexpr bool PQ = PK_PACKQ != 0 && STG != 0 && sizeof(T) == 8 && !DEAL && (BOUND == 192 || BOUND == 320 || BOUND == 384);
     unsigned char *const gstage = STG == 1 ? nullptr : a.stage + (size_t)blockIdx.x * (size_t)a.stage_stride;
     unsigned char *sA = STAGED ? smem : gstage;                // ROW part of the row tree (its records are patched in place)
     unsigned char *sB = STG == 1 ? smem + a.tree_region : STG == 2 ? gstage : gstage + a.tree_region;   // COLUMN part of the column tree
@@ -549,7 +597,7 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
         if (OVRQ && !CSMEM && tid < PK_PAD_RECORDS) {     // never-matching records after the last row (see PK_OVERRUN)
             int4 *padrec = reinterpret_cast<int4 *>(sA + bytesR) + 2 * tid;
             padrec[0] = make_int4(0, 0, 0, 0);
-            padrec[1] = make_int4(0, 0, 0, 0xffff);
+            padrec[1] = PQ ? make_int4((int)0xff000000u, (int)0xff000000u, 0, 0xffff) : make_int4(0, 0, 0, 0xffff);
         }
 
         const int *hA = reinterpret_cast<const int *>(sA);
@@ -608,9 +656,14 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
             const int c = (pk >> 24) & 0xff, p = (pk >> 16) & 0xff;
             const int o0 = (pk & 0xff) ? rowoff[rec->off0] : 0;
             const int o1 = (pk & 0xff00) ? rowoff[rec->off1] : 0;
-            rec->off0 = o0;
-            rec->off1 = o1;
-            rec->st_off = rowoff[r] - (gstB[c * npc + p] - clsB[c]);       // + column position in the class = stored cell
+            const int so = rowoff[r] - (gstB[c * npc + p] - clsB[c]);      // + column position in the class = stored cell
+            rec->off0 = PQ ? (o0 | ((pk & 0xff) << 24)) : o0;              // PQ: the child's class + 1 in the top byte
+            rec->off1 = PQ ? (o1 | ((pk & 0xff00) << 16)) : o1;
+            rec->st_off = so;
+            if constexpr (PQ && sizeof(T) == 4) {
+                rec->st2 = so;
+                rec->pk2 = pk;
+            }
             rec->a0 *= (T)a.bscale;                // lengths in units that make the squared distance the exponent
             rec->a1 *= (T)a.bscale;
         }
@@ -658,19 +711,19 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
         T part;                                                                                                       \
         switch ((D).flags & (512 | 1024)) {               /* bit 9 / 10: slot 0 / 1 is a tip in every row of the class */ \
         case 512 | 1024:                                                                                              \
-            part = pk_rect<T, CSMEM, STAGED, false, false, U, DEAL || PK_FENCE_ALL, OVRQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,   \
+            part = pk_rect<T, CSMEM, STAGED, false, false, U, DEAL || PK_FENCE_ALL, OVRQ, PQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,   \
                                                             cells, gk, sigma, tipf);                                  \
             break;                                                                                                    \
         case 512:                                                                                                     \
-            part = pk_rect<T, CSMEM, STAGED, false, true, U, DEAL || PK_FENCE_ALL, OVRQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,    \
+            part = pk_rect<T, CSMEM, STAGED, false, true, U, DEAL || PK_FENCE_ALL, OVRQ, PQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,    \
                                                            cells, gk, sigma, tipf);                                   \
             break;                                                                                                    \
         case 1024:                                                                                                    \
-            part = pk_rect<T, CSMEM, STAGED, true, false, U, DEAL || PK_FENCE_ALL, OVRQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,    \
+            part = pk_rect<T, CSMEM, STAGED, true, false, U, DEAL || PK_FENCE_ALL, OVRQ, PQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,    \
                                                            cells, gk, sigma, tipf);                                   \
             break;                                                                                                    \
         default:                                                                                                      \
-            part = pk_rect<T, CSMEM, STAGED, true, true, U, DEAL || PK_FENCE_ALL, OVRQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,     \
+            part = pk_rect<T, CSMEM, STAGED, true, true, U, DEAL || PK_FENCE_ALL, OVRQ, PQ>(rp, (D).rows, (JB), b0, b1, codeB0[col], codeB1[col], pkey,     \
                                                           cells, gk, sigma, tipf);                                    \
         }                                                                                                             \
         acc += (double)part;                                                                                          \
@@ -1547,6 +1600,8 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
         if (PK_OVERRUN)
             for (size_t g = 0; g < fa->max_gcnt.size(); ++g) slack = std::max<long long>(slack, std::max(fa->max_gcnt[g], fb->max_gcnt[g]));
         args.slab_elems = ((((maxM + slack) * (long long)w) + 255) & ~255ll) / (long long)w;
+        if (PK_PACKQ && stg != 0 && !prec32 && args.slab_elems >= (1ll << 24))
+            return pk_fail(PK_ERR_INVALID, "internal: staged pair with more than 2^24 stored cells");
         if (args.slab_elems >= (1ll << 31))
             return pk_fail(PK_ERR_INVALID, "tree pair too large: " + std::to_string(args.slab_elems) + " stored cells exceed the 32-bit cell index");
         // Every resident CTA owns one slab.  Huge pairs (tens of thousands of tips: hundreds of MB per slab) run on fewer
