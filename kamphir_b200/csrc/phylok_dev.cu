@@ -299,6 +299,9 @@ __device__ __forceinline__ int4 ld_int4(const int4 *p) {
 #ifndef PK_PACKQ
 #define PK_PACKQ 1
 #endif
+#ifndef PK_QMASK
+#define PK_QMASK 0x7f000000
+#endif
 template <bool STAGED>
 __device__ __forceinline__ int2 ld_int2(const int2 *p) {
     int2 v;
@@ -307,8 +310,10 @@ __device__ __forceinline__ int2 ld_int2(const int2 *p) {
     return v;
 }
 // child cell of slot 0 / 1: the stored cell when the children's classes agree, else cell 1 (= 1, productions differ)
-#define PK_GATHER0(q) (PQ ? C.ld((((q).x ^ qb0) & 0xff000000) == 0 ? (q).x + kb0 : 1) : C.ld((((q).w ^ qb0) & 0xff) == 0 ? (q).x + kb0 : 1))
-#define PK_GATHER1(q) (PQ ? C.ld((((q).y ^ qb1) & 0xff000000) == 0 ? (q).y + kb1 : 1) : C.ld((((q).w ^ qb1) & 0xff00) == 0 ? (q).y + kb1 : 1))
+// (PQ: the mask leaves bit 31 out -- class + 1 <= 65 needs 7 bits -- so that the test cannot be rewritten as an unsigned
+// compare of the xor, which costs two instructions; as it stands it is one LOP3 with a predicate result)
+#define PK_GATHER0(q) (PQ ? C.ld((((q).x ^ qb0) & PK_QMASK) == 0 ? (q).x + kb0 : 1) : C.ld((((q).w ^ qb0) & 0xff) == 0 ? (q).x + kb0 : 1))
+#define PK_GATHER1(q) (PQ ? C.ld((((q).y ^ qb1) & PK_QMASK) == 0 ? (q).y + kb1 : 1) : C.ld((((q).w ^ qb1) & 0xff00) == 0 ? (q).y + kb1 : 1))
 // the part of a row record the gathers need: PQ: {offset | class << 24} of both children (8 bytes), else the whole second half
 #define PK_LOADQ(ptr)                                                                                   \
     int4 q;                                                                                             \
@@ -510,7 +515,8 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
     // 192-thread tier (200-550 tips: 468 against 460 Gcells/s at 500 tips, 348 against 342 at 200), the 320-thread tier
     // (800 tips: 442 against 425) and the 384-thread one (1000 tips: 434 against 432).  fp32 (788 against 805 at 500 tips),
     // the 64-thread tier, the big CTAs (2000 tips: 422 against 437) and the labelled variant lose with it.
-    constexpr bool PQ = PK_PACKQ != 0 && STG != 0 && sizeof(T) == 8 && !DEAL && (BOUND == 192 || BOUND == 320 || BOUND == 384);
+    constexpr bool PQ = PK_PACKQ != 0 && STG != 0 &&
+                        (PK_PACKQ == 2 || (sizeof(T) == 8 && !DEAL && (BOUND == 192 || BOUND == 320 || BOUND == 384)));
     unsigned char *const gstage = STG == 1 ? nullptr : a.stage + (size_t)blockIdx.x * (size_t)a.stage_stride;
     unsigned char *sA = STAGED ? smem : gstage;                // ROW part of the row tree (its records are patched in place)
     unsigned char *sB = STG == 1 ? smem + a.tree_region : STG == 2 ? gstage : gstage + a.tree_region;   // COLUMN part of the column tree
@@ -1600,7 +1606,7 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
         if (PK_OVERRUN)
             for (size_t g = 0; g < fa->max_gcnt.size(); ++g) slack = std::max<long long>(slack, std::max(fa->max_gcnt[g], fb->max_gcnt[g]));
         args.slab_elems = ((((maxM + slack) * (long long)w) + 255) & ~255ll) / (long long)w;
-        if (PK_PACKQ && stg != 0 && !prec32 && args.slab_elems >= (1ll << 24))
+        if (PK_PACKQ && stg != 0 && args.slab_elems >= (1ll << 24))
             return pk_fail(PK_ERR_INVALID, "internal: staged pair with more than 2^24 stored cells");
         if (args.slab_elems >= (1ll << 31))
             return pk_fail(PK_ERR_INVALID, "tree pair too large: " + std::to_string(args.slab_elems) + " stored cells exceed the 32-bit cell index");
