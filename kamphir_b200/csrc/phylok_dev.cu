@@ -436,9 +436,6 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
 #ifndef PK_UNROLL
 #define PK_UNROLL 4
 #endif
-#ifndef PK_DISCARD
-#define PK_DISCARD 0                // 1: discard a pair's stored cells from L2 when the pair is done (no write-back of dead cells)
-#endif
 #ifndef PK_COLGLOBAL_DEFAULT
 #define PK_COLGLOBAL_DEFAULT 0      // COLUMN part in the global staging area for the pairs that fit one CTA per SM otherwise
 #endif
@@ -499,9 +496,6 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ long long s_work[2];
-#if PK_DISCARD
-    __shared__ int s_used;
-#endif
     __shared__ int s_cntB[PK_MAX_CLASSES];
     __shared__ double s_part[32];
     __shared__ __align__(16) LevelDesc s_desc[PK_DESC_MAX];
@@ -651,9 +645,6 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
                 if (r < nA) rowoff[r] = carry + incl - len;
                 carry += __shfl_sync(0xffffffffu, incl, 31);
             }
-#if PK_DISCARD
-            if (lane == 0) s_used = carry;      // cells this pair stores
-#endif
         }
         __syncthreads();
         for (int r = tid; r < nA; r += NT) {      // patch the staged records with this pair's C offsets
@@ -786,17 +777,6 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
                 a.out[ia] = k;
             }
         }
-#if PK_DISCARD
-        // The stored cells of this pair are dead: every one of them has been read (at most once) by now.  Telling L2 so
-        // keeps them from being written back to HBM when the next pairs push them out (0.25 MB of DRAM writes per 500-tip
-        // pair otherwise, 88 % of the kernel's DRAM traffic).  A discard is a weak write: the barrier at the top of the loop
-        // orders it before the next pair's stores to the same lines.
-        if (!CSMEM) {
-            const int nlines = (int)(((long long)s_used * (long long)sizeof(T) + 127) >> 7);
-            for (int ln = tid; ln < nlines; ln += NT)
-                asm volatile("discard.global.L2 [%0], 128;" ::"l"(cells.base + ((unsigned long long)ln << 7)) : "memory");
-        }
-#endif
         // the next iteration's first __syncthreads orders these reads before the staging buffers are overwritten
     }
 }
