@@ -127,6 +127,9 @@ __device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity) {
 // 16 j + (l & 15)): a 64-bit LDS is served per half-warp, so every lookup is conflict-free.  The U chains are written
 // stage by stage so the scheduler interleaves them.
 #define PK_EXP_TAB 64
+#ifndef PK_TAB_VOLATILE
+#define PK_TAB_VOLATILE 0
+#endif
 #define PK_EXP_REP 16
 __constant__ double pk_poly[4] = {-0x1.62e42fefa2417p-7, 0x1.ebfbdff82bb76p-15, -0x1.c6b0b9214b9aep-23,
                                   0x1.3b2acb2c36b23p-31};   // 2^(-r/64) = 1 + r (c1 + c2 r + c3 r^2 + c4 r^3)
@@ -135,6 +138,9 @@ struct GaussK {
     uint32_t tab_addr;   // shared-memory address of this lane's copy of table entry 0
     int clamp_hi;        // high word of the largest E that keeps the result normal
     T lambda, neg_inv_tau;
+    uint32_t extra_addr; // shared-memory address of {sigma, -, c3, c4} behind the table
+    bool regc;           // pk_rect2: the two highest polynomial coefficients come in registers (c3, c4), read from shared memory
+    double c3, c4;       // with a volatile load so that ptxas cannot re-read them from the constant bank in every iteration
 };
 template <int U>
 __device__ __forceinline__ void pk_gauss(const double (&E)[U], double (&out)[U], const GaussK<double> &gk) {
@@ -147,7 +153,7 @@ __device__ __forceinline__ void pk_gauss(const double (&E)[U], double (&out)[U],
 #pragma unroll
     for (int u = 0; u < U; ++u) r[u] = (t[u] - 6755399441055744.0) + Ec[u];
 #pragma unroll
-    for (int u = 0; u < U; ++u) q[u] = fma(pk_poly[3], r[u], pk_poly[2]);
+    for (int u = 0; u < U; ++u) q[u] = gk.regc ? fma(gk.c4, r[u], gk.c3) : fma(pk_poly[3], r[u], pk_poly[2]);
 #pragma unroll
     for (int u = 0; u < U; ++u) q[u] = fma(q[u], r[u], pk_poly[1]);
 #pragma unroll
@@ -159,7 +165,11 @@ __device__ __forceinline__ void pk_gauss(const double (&E)[U], double (&out)[U],
         const int k = __double2loint(t[u]);
         unsigned lo;
         int hi;
+#if PK_TAB_VOLATILE      // volatile: stays behind the child-cell gathers issued before the Gaussians (volatile asms keep their order)
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(gk.tab_addr + ((k & (PK_EXP_TAB - 1)) << 7)));
+#else
         asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(gk.tab_addr + ((k & (PK_EXP_TAB - 1)) << 7)));
+#endif
         out[u] = q[u] * __hiloint2double(hi + (k << 14), (int)lo);
     }
 }
@@ -216,6 +226,11 @@ static_assert(PK_DESC_MAX >= PK_MAX_CLASSES, "one level's descriptors (one per c
 // ---------------------------------------------------------------------------------------------------
 // -DPK_DEBUG_BOUNDS (scripts/bounds_check.sh; compute-sanitizer is not available on the GPU pool): every cell index is
 // checked against the slab / shared-memory array size, violations are counted and the launch fails.
+#ifndef PK_ST_NOCLOBBER
+#define PK_ST_CLOBBER : "memory"
+#else
+#define PK_ST_CLOBBER
+#endif
 template <typename T, bool CSMEM>
 struct Cells {
     T *sm;
@@ -249,8 +264,8 @@ struct Cells {
             return;
         }
         const unsigned long long addr = base + (unsigned long long)(unsigned)idx * sizeof(T);
-        if (sizeof(T) == 8) asm volatile("st.global.f64 [%0], %1;" ::"l"(addr), "d"(*reinterpret_cast<double *>(&v)) : "memory");
-        else asm volatile("st.global.f32 [%0], %1;" ::"l"(addr), "f"(*reinterpret_cast<float *>(&v)) : "memory");
+        if (sizeof(T) == 8) asm volatile("st.global.f64 [%0], %1;" ::"l"(addr), "d"(*reinterpret_cast<double *>(&v)) PK_ST_CLOBBER);
+        else asm volatile("st.global.f32 [%0], %1;" ::"l"(addr), "f"(*reinterpret_cast<float *>(&v)) PK_ST_CLOBBER);
     }
 };
 
@@ -431,6 +446,157 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
 }
 
 // ---------------------------------------------------------------------------------------------------
+// pk_rect2: the same rectangle walk for the unlabelled fp64 tiers with both tree parts in shared memory and C in an HBM
+// slab, written against instruction count (round 2, second half).
+//  * The row records are addressed by their 32-bit shared-memory address and the loop runs on that address alone (end
+//    test = one compare, prefetch clamp = one minimum).
+//  * Every cell address is ONE IMAD.WIDE.U32 onto a per-lane 64-bit base that already holds the lane's part of the index.
+//    The cell indices of such a kernel start at PK_XOFF instead of 0 (cells.base is moved down by as much), the patched
+//    record words carry a tag in their top byte -- class + 1 of the child in the two offset words, the parent code in the
+//    store word -- and the lane's bases are moved down by its own tag:
+//      gather slot s :  bk_s = slab + 8 * (rank_s - tag_s),  word + rank_s - tag_s = the child's cell when the tags agree;
+//                       otherwise the lane selects alt_s = tag_s + (PK_XOFF + 1 - rank_s), which leads from bk_s to the cell
+//                       that holds 1 -- and whose top byte is tag_s again (PK_XOFF + 1 >= any rank), so alt_s is also the
+//                       word the class test compares with: LOP3 (predicate), SEL, IMAD.WIDE, LDG per gather
+//      store         :  bj = slab + 8 * (column - tag), word + column - tag = the stored cell: LOP3, IMAD.WIDE, STG
+// ---------------------------------------------------------------------------------------------------
+#ifndef PK_RECT2
+#define PK_RECT2 1
+#endif
+#ifndef PK_R2_FENCE
+#define PK_R2_FENCE 0
+#endif
+#define PK_XOFF 16384          // >= the largest rank of a node in its (class, parent code) group; offsets stay below 2^24
+__device__ __forceinline__ void lds_f64x2(uint32_t a, double &x, double &y) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+}
+__device__ __forceinline__ int lds_i32(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int2 lds_i32x2(uint32_t a) {
+    int2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ unsigned long long cell_addr(unsigned long long b, int idx) {     // one IMAD.WIDE.U32
+    return b + (unsigned long long)(unsigned)idx * 8ull;
+}
+__device__ __forceinline__ double ldg_cell(unsigned long long b, int idx) {
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(cell_addr(b, idx)));
+    return v;
+}
+__device__ __forceinline__ void stg_cell(unsigned long long b, int idx, double v) {
+    asm volatile("st.global.f64 [%0], %1;" ::"l"(cell_addr(b, idx)), "d"(v) : "memory");
+}
+template <bool G0, bool G1, int U>
+__device__ __forceinline__ double pk_rect2(uint32_t ra, int rows, int jb, double b0, double b1, int cb0, int cb1, int pcode,
+                                           unsigned long long base, const GaussK<double> &gk_in, double sigma, double tipf, double part) {
+#ifndef PK_R2_SIGMA_REG
+#define PK_R2_SIGMA_REG 1
+#endif
+    const int tag0 = (int)((unsigned)cb0 & 0xff000000u), tag1 = (int)((unsigned)cb1 & 0xff000000u);
+    const int rank0 = cb0 & 0xffffff, rank1 = cb1 & 0xffffff;
+    unsigned long long bk0 = base + (unsigned long long)((long long)(rank0 - tag0) * 8);
+    unsigned long long bk1 = base + (unsigned long long)((long long)(rank1 - tag1) * 8);
+    int alt0 = tag0 + (PK_XOFF + 1 - rank0), alt1 = tag1 + (PK_XOFF + 1 - rank1);
+    const int ptag = pcode << 24;
+    unsigned long long bj = base + (unsigned long long)((long long)(jb - ptag) * 8);
+#if PK_R2_SIGMA_REG
+    // sigma and the two highest polynomial coefficients stay in register pairs: read from shared memory with volatile loads,
+    // which ptxas cannot repeat (it otherwise re-reads them from the constant bank in every iteration)
+    GaussK<double> gk = gk_in;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(sigma) : "r"(gk.extra_addr));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(gk.c3), "=d"(gk.c4) : "r"(gk.extra_addr + 16u));
+    gk.regc = true;
+#else
+    const GaussK<double> &gk = gk_in;
+#endif
+    // opaque and pinned here: kept in registers as they are, not re-derived per access
+    if (G0) asm volatile("" : "+l"(bk0), "+r"(alt0));
+    if (G1) asm volatile("" : "+l"(bk1), "+r"(alt1));
+    asm volatile("" : "+l"(bj));
+#define PK2_G0(w) ldg_cell(bk0, (((w) ^ alt0) & PK_QMASK) == 0 ? (w) : alt0)
+#define PK2_G1(w) ldg_cell(bk1, (((w) ^ alt1) & PK_QMASK) == 0 ? (w) : alt1)
+    double cf = 1.0;                                                       // factor of the slots that are tips in every row
+    if (!G0) cf = tag0 == 0 ? tipf : 1.0;
+    if (!G1) cf *= tag1 == 0 ? tipf : 1.0;
+    double f0[U], f1[U];                                              // part: the thread's running sum over the pair, passed through
+    const uint32_t rend = ra + 32u * (uint32_t)(rows & ~(U - 1));     // first record after the full groups
+    const uint32_t rlast = rend - 32u * U;                            // the last full group (prefetch clamp)
+    if ((G0 || G1) && ra != rend) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int2 q = lds_i32x2(ra + 32u * u + 16);
+            if (G0) f0[u] = PK2_G0(q.x);
+            if (G1) f1[u] = PK2_G1(q.y);
+        }
+    }
+    for (; ra != rend; ra += 32u * U) {
+        double x[U], ev[U], g[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            double a0, a1;
+            lds_f64x2(ra + 32u * u, a0, a1);
+            const double d0 = a0 - b0, d1 = a1 - b1;
+            x[u] = fma(d1, d1, d0 * d0);
+            g[u] = G0 ? (G1 ? f0[u] * f1[u] : f0[u] * cf) : (G1 ? f1[u] * cf : cf);
+        }
+        if (G0 || G1) {      // the next group's gathers before this group's Gaussians (the last group re-reads itself)
+            const uint32_t np = min(ra + 32u * U, rlast);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int2 q = lds_i32x2(np + 32u * u + 16);
+                if (G0) f0[u] = PK2_G0(q.x);
+                if (G1) f1[u] = PK2_G1(q.y);
+            }
+#if PK_R2_FENCE      // memory operations do not cross a warp barrier: the gathers stay in front of the Gaussians (ptxas otherwise sinks
+            __syncwarp(__activemask());      // them to the end of the loop body, a dozen instructions before their first use)
+#endif
+        }
+        pk_gauss<U>(x, ev, gk);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int sw = lds_i32(ra + 32u * u + 24);                 // store offset | parent code << 24
+            if (((sw ^ ptag) & PK_QMASK) == 0) stg_cell(bj, sw, fma(ev[u], g[u], sigma));
+            part = fma(ev[u], g[u], part);
+        }
+    }
+    const int rem = rows & (U - 1);
+    if (U > 1 && rem > 0) {
+        if (G0 || G1) {
+#pragma unroll
+            for (int u = 0; u < U - 1; ++u) {
+                if (u < rem) {
+                    const int2 q = lds_i32x2(ra + 32u * u + 16);
+                    if (G0) f0[u] = PK2_G0(q.x);
+                    if (G1) f1[u] = PK2_G1(q.y);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U - 1; ++u) {
+            if (u < rem) {
+                double a0, a1;
+                lds_f64x2(ra + 32u * u, a0, a1);
+                const double d0 = a0 - b0, d1 = a1 - b1;
+                double x1[1] = {fma(d1, d1, d0 * d0)}, e1[1];
+                pk_gauss<1>(x1, e1, gk);
+                const double g = G0 ? (G1 ? f0[u] * f1[u] : f0[u] * cf) : (G1 ? f1[u] * cf : cf);
+                const int sw = lds_i32(ra + 32u * u + 24);
+                if (((sw ^ ptag) & PK_QMASK) == 0) stg_cell(bj, sw, fma(e1[0], g, sigma));
+                part = fma(e1[0], g, part);
+            }
+        }
+    }
+    return part;
+#undef PK2_G0
+#undef PK2_G1
+}
+
+// ---------------------------------------------------------------------------------------------------
 // the DP kernel
 // ---------------------------------------------------------------------------------------------------
 #ifndef PK_UNROLL
@@ -496,10 +662,12 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ long long s_work[2];
+    __shared__ int s_pair[2];
+    __shared__ __align__(8) int s_state[4];      // pk_rect2: parity, first level of the batch, slab base
     __shared__ int s_cntB[PK_MAX_CLASSES];
     __shared__ double s_part[32];
     __shared__ __align__(16) LevelDesc s_desc[PK_DESC_MAX];
-    __shared__ __align__(16) unsigned long long s_tab[sizeof(T) == 8 ? PK_EXP_TAB * PK_EXP_REP : 2];
+    __shared__ __align__(16) unsigned long long s_tab[sizeof(T) == 8 ? PK_EXP_TAB * PK_EXP_REP + 4 : 2];   // + sigma, -, c3, c4 (pk_rect2)
 
     int tid;                                                   // opaque read: lives in a register, never re-read via S2R
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
@@ -509,8 +677,10 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
     // 192-thread tier (200-550 tips: 468 against 460 Gcells/s at 500 tips, 348 against 342 at 200), the 320-thread tier
     // (800 tips: 442 against 425) and the 384-thread one (1000 tips: 434 against 432).  fp32 (788 against 805 at 500 tips),
     // the 64-thread tier, the big CTAs (2000 tips: 422 against 437) and the labelled variant lose with it.
-    constexpr bool PQ = PK_PACKQ != 0 && STG != 0 &&
-                        (PK_PACKQ == 2 || (sizeof(T) == 8 && !DEAL && (BOUND == 192 || BOUND == 320 || BOUND == 384)));
+    constexpr bool RECT2 = PK_RECT2 != 0 && sizeof(T) == 8 && !CSMEM && !DEAL && STG == 1;      // pk_rect2 (see there)
+    constexpr int XO = RECT2 ? PK_XOFF : 0;                    // index of the first cell
+    constexpr bool PQ = RECT2 || (PK_PACKQ != 0 && STG != 0 &&
+                        (PK_PACKQ == 2 || (sizeof(T) == 8 && !DEAL && (BOUND == 192 || BOUND == 320 || BOUND == 384))));
     unsigned char *const gstage = STG == 1 ? nullptr : a.stage + (size_t)blockIdx.x * (size_t)a.stage_stride;
     unsigned char *sA = STAGED ? smem : gstage;                // ROW part of the row tree (its records are patched in place)
     unsigned char *sB = STG == 1 ? smem + a.tree_region : STG == 2 ? gstage : gstage + a.tree_region;   // COLUMN part of the column tree
@@ -519,7 +689,7 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
     const unsigned long long slab_off = (unsigned long long)blockIdx.x * (unsigned long long)a.slab_elems;
     Cells<T, CSMEM> cells;
     cells.sm = reinterpret_cast<T *>(smem + info_at + a.rowinfo_bytes);
-    cells.base = (unsigned long long)(reinterpret_cast<T *>(a.scratch) + slab_off);
+    cells.base = (unsigned long long)(reinterpret_cast<T *>(a.scratch) + slab_off) - (unsigned long long)XO * sizeof(T);
 #ifdef PK_DEBUG_BOUNDS
     cells.limit = (unsigned)a.slab_elems;
     cells.err = a.counter + 1;
@@ -527,6 +697,12 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
     if (tid == 0) mbar_init(&s_bar, 1);
     if (sizeof(T) == 8)
         for (int i = tid; i < PK_EXP_TAB * PK_EXP_REP; i += NT) s_tab[i] = a.exp_tab[i / PK_EXP_REP];
+    if (sizeof(T) == 8 && tid == 0) {
+        double *extra = reinterpret_cast<double *>(&s_tab[sizeof(T) == 8 ? PK_EXP_TAB * PK_EXP_REP : 0]);
+        extra[0] = a.sigma;
+        extra[2] = pk_poly[2];
+        extra[3] = pk_poly[3];
+    }
     if (tid < 32) s_part[tid] = 0.0;
     __syncthreads();
     // the slab base plus a zero read from a lane-dependent shared-memory address: ptxas cannot prove the sum uniform, so it stays in a vector
@@ -541,11 +717,28 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
     gk.clamp_hi = a.clamp_hi;
     gk.lambda = lambda;
     gk.neg_inv_tau = (T)a.neg_inv_tau;
+    gk.extra_addr = smem_u32(s_tab) + (sizeof(T) == 8 ? PK_EXP_TAB * PK_EXP_REP * 8u : 0u);
+    gk.regc = false;
+    gk.c3 = gk.c4 = 0.0;
+    GaussK<double> gk2;                                        // pk_rect2 is fp64 only (the copy is dead code elsewhere)
+    gk2.tab_addr = gk.tab_addr;
+    gk2.clamp_hi = gk.clamp_hi;
+    gk2.lambda = a.lambda;
+    gk2.neg_inv_tau = a.neg_inv_tau;
+    gk2.extra_addr = gk.extra_addr;
+    gk2.regc = false;
+    gk2.c3 = gk2.c4 = 0.0;
 
+    if (RECT2 && tid == 0) {      // pk_rect2 kernels keep per-CTA state in shared memory instead of registers (see the wavefront)
+        s_state[0] = 0;           // mbarrier parity of the next staging
+        s_state[1] = 0;           // first level of the current descriptor batch
+        *reinterpret_cast<unsigned long long *>(&s_state[2]) = cells.base;
+    }
     for (unsigned it_no = 0;; ++it_no) {
-        if (tid == 0) s_work[it_no & 1] = (long long)atomicAdd(a.counter, 1ull);
+        const int slot = RECT2 ? 0 : (int)(it_no & 1);      // RECT2: one slot (every path to the next iteration passes a barrier after the read)
+        if (tid == 0) s_work[slot] = (long long)atomicAdd(a.counter, 1ull);
         __syncthreads();
-        const long long w = s_work[it_no & 1];
+        const long long w = s_work[slot];
         if (w >= a.total) break;
 
         // ---- which pair ------------------------------------------------------------------------
@@ -561,7 +754,10 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
             const int2 t = a.tiles[tile];
             ia = (t.x << sh) + (r >> sh);
             ib = (t.y << sh) + (r & ((1 << sh) - 1));
-            if (ib < ia || ib >= a.n_trees || ia >= a.n_trees) continue;
+            if (ib < ia || ib >= a.n_trees || ia >= a.n_trees) {
+                if (RECT2) __syncthreads();      // everybody has read s_work[0] before thread 0 overwrites it
+                continue;
+            }
         } else {
             ia = ib = (int)w;
         }
@@ -591,8 +787,12 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
             __syncthreads();
         }
         if (STAGED) {
-            mbar_wait(&s_bar, parity);
-            parity ^= 1;
+            if constexpr (RECT2) {
+                mbar_wait(&s_bar, (uint32_t) * reinterpret_cast<volatile int *>(&s_state[0]));      // flipped by thread 0 behind the next barrier
+            } else {
+                mbar_wait(&s_bar, parity);
+                parity ^= 1;
+            }
         }
         if (OVRQ && !CSMEM && tid < PK_PAD_RECORDS) {     // never-matching records after the last row (see PK_OVERRUN)
             int4 *padrec = reinterpret_cast<int4 *>(sA + bytesR) + 2 * tid;
@@ -622,12 +822,12 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
         //      contiguous column group with its own parent code: R cells per pair instead of M.
         if (tid < ncls) s_cntB[tid] = clsB[tid + 1] - clsB[tid];      // the host launches at least as many threads as classes
         if (tid == 0) {
-            cells.st(0, tipf);       // tip x tip child factor (phyloK2.py:194-196)
-            cells.st(1, (T)1);       // factor of a child slot whose productions differ (phyloK2.py:191-192)
+            cells.st(XO, tipf);      // tip x tip child factor (phyloK2.py:194-196)
+            cells.st(XO + 1, (T)1);  // factor of a child slot whose productions differ (phyloK2.py:191-192)
         }
         // row offsets: exclusive scan of the stored row lengths, by warp 0 (32 rows per step, running carry)
         if (warp == 0) {
-            int carry = 2;
+            int carry = 2 + XO;
             for (int base = 0; base < nA; base += 32) {
                 const int r = base + lane;
                 int len = 0;
@@ -647,16 +847,17 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
             }
         }
         __syncthreads();
+        if (RECT2 && tid == 0) s_state[0] ^= 1;   // everybody is past this pair's mbarrier wait
         for (int r = tid; r < nA; r += NT) {      // patch the staged records with this pair's C offsets
             RowRec<T> *rec = rowrec + r;
             const int pk = rec->packed;
             const int c = (pk >> 24) & 0xff, p = (pk >> 16) & 0xff;
-            const int o0 = (pk & 0xff) ? rowoff[rec->off0] : 0;
-            const int o1 = (pk & 0xff00) ? rowoff[rec->off1] : 0;
+            const int o0 = (pk & 0xff) ? rowoff[rec->off0] : XO;
+            const int o1 = (pk & 0xff00) ? rowoff[rec->off1] : XO;
             const int so = rowoff[r] - (gstB[c * npc + p] - clsB[c]);      // + column position in the class = stored cell
             rec->off0 = PQ ? (o0 | ((pk & 0xff) << 24)) : o0;              // PQ: the child's class + 1 in the top byte
             rec->off1 = PQ ? (o1 | ((pk & 0xff00) << 16)) : o1;
-            rec->st_off = so;
+            rec->st_off = RECT2 ? (so | (p << 24)) : so;       // pk_rect2: the parent code rides in the top byte
             if constexpr (PQ && sizeof(T) == 4) {
                 rec->st2 = so;
                 rec->pk2 = pk;
@@ -675,6 +876,86 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
 
         // ---- wavefront over the row tree's levels, a batch of levels at a time -------------------------
         double acc = 0.0;
+        if constexpr (RECT2) {
+            // Same walk as the generic code below, written so that nothing but the running sum, the thread index and the loop
+            // counters stays in registers across the row loops: whatever comes from the staged headers is read again where it
+            // is needed (lds_i32 is volatile: not hoisted), the descriptors carry the shared-memory address of a rectangle's
+            // first record, and the epilogue finds the pair in shared memory.  The row loops then keep their constants in
+            // registers instead of re-reading them every iteration (64 registers per thread at 5 CTAs per SM).
+            const uint32_t sA32 = smem_u32(sA), sB32 = smem_u32(sB);
+            if (tid == 0) {
+                s_pair[0] = ia;
+                s_pair[1] = ib;
+                s_state[1] = 0;
+            }
+            for (;;) {
+                __syncthreads();                       // previous batch done with s_desc; patched records, s_state visible
+                const int L0 = *reinterpret_cast<volatile int *>(&s_state[1]);
+                if (L0 >= lds_i32(sA32 + 8)) break;
+                {
+                    const int nlev = lds_i32(sA32 + 8), L1 = min(nlev, L0 + PK_DESC_MAX / 3);
+                    const uint32_t lvl32 = sA32 + lds_i32(sA32 + 20), rec32 = sA32 + lds_i32(sA32 + 24), cls32 = sB32 + lds_i32(sB32 + 16);
+                    const unsigned tip0 = lds_i32(sA32 + 28), tip1 = lds_i32(sA32 + 36);
+                    const int ncls_a = lds_i32(sA32 + 4);              // unlabelled trees: at most 3 classes, the descriptors of a level take 3 slots
+                    for (int L = L0 + tid; L < L1; L += NT) {          // one thread per level describes its rectangles
+                        LevelDesc *dst = s_desc + (L - L0) * 3;
+                        int last = -1;
+                        for (int c = 0; c < 3; ++c) {
+                            LevelDesc d;
+                            d.r0 = 0; d.rows = 0; d.wB = 0; d.colbase = 0; d.flags = 0; d.nchunks = 0; d.chunk_end = 0; d.pad1 = 0;
+                            if (c < ncls_a) {
+                                const int r0 = lds_i32(lvl32 + 4 * (c * (nlev + 1) + L)), rows = lds_i32(lvl32 + 4 * (c * (nlev + 1) + L + 1)) - r0;
+                                const int wB = s_cntB[c];
+                                d.r0 = r0; d.wB = wB; d.colbase = lds_i32(cls32 + 4 * c);
+                                d.pad1 = (int)(rec32 + 32u * (uint32_t)r0);          // shared-memory address of the first record
+                                if (rows > 0 && wB > 0) {
+                                    d.rows = rows;
+                                    d.flags = (((tip0 >> c) & 1u) ? 512 : 0) | (((tip1 >> c) & 1u) ? 1024 : 0);
+                                    last = c;
+                                }
+                            }
+                            if (c == 2 && L == L1 - 1) d.flags |= 2048;      // last descriptor of the batch
+                            dst[c] = d;
+                        }
+                        if (last >= 0) dst[last].flags |= 256;
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) s_state[1] = L0 + PK_DESC_MAX / 3;       // read again behind the barrier at the loop's head
+                for (uint32_t dp = smem_u32(s_desc);; dp += (uint32_t)sizeof(LevelDesc)) {      // fields: r0, rows, wB, colbase, chunk_end, flags, nchunks, pad1
+                    const int rows = lds_i32(dp + 4);
+                    if (rows > 0) {                    // uniform
+                        for (int jb = tid; jb < lds_i32(dp + 8); jb += NT) {
+                            const uint32_t col = (uint32_t)(lds_i32(dp + 12) + jb);
+                            double b0, b1;
+                            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b0) : "r"(sB32 + lds_i32(sB32 + 24) + 8u * col));
+                            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b1) : "r"(sB32 + lds_i32(sB32 + 28) + 8u * col));
+                            const int cb0 = lds_i32(sB32 + lds_i32(sB32 + 32) + 4u * col), cb1 = lds_i32(sB32 + lds_i32(sB32 + 36) + 4u * col);
+                            const int pc = lds_i32(sB32 + lds_i32(sB32 + 40) + 4u * col);
+                            const uint32_t ra = (uint32_t)lds_i32(dp + 28);
+                            unsigned long long base;
+                            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(base) : "r"(smem_u32(&s_state[2])));
+                            switch (lds_i32(dp + 20) & (512 | 1024)) {               // bit 9 / 10: slot 0 / 1 is a tip in every row of the class
+                            case 512 | 1024:
+                                acc = pk_rect2<false, false, U>(ra, rows, jb, b0, b1, cb0, cb1, pc, base, gk2, a.sigma, a.sigma + a.lambda, acc);
+                                break;
+                            case 512:
+                                acc = pk_rect2<false, true, U>(ra, rows, jb, b0, b1, cb0, cb1, pc, base, gk2, a.sigma, a.sigma + a.lambda, acc);
+                                break;
+                            case 1024:
+                                acc = pk_rect2<true, false, U>(ra, rows, jb, b0, b1, cb0, cb1, pc, base, gk2, a.sigma, a.sigma + a.lambda, acc);
+                                break;
+                            default:
+                                acc = pk_rect2<true, true, U>(ra, rows, jb, b0, b1, cb0, cb1, pc, base, gk2, a.sigma, a.sigma + a.lambda, acc);
+                            }
+                        }
+                    }
+                    const int fl = lds_i32(dp + 20);
+                    if (rows > 0 && (fl & 256)) __syncthreads();      // end of a level: its cells are final before the next one reads
+                    if (fl & 2048) break;
+                }
+            }
+        } else {
         const int lev_per_batch = max(1, PK_DESC_MAX / ncls);
         for (int L0 = 0; L0 < nlevA; L0 += lev_per_batch) {
             const int L1 = min(nlevA, L0 + lev_per_batch);
@@ -755,6 +1036,7 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
             }
         }
 #undef PK_COLUMN
+        }
 
         // ---- deterministic block reduction of K ---------------------------------------------------
 #pragma unroll
@@ -762,13 +1044,17 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
         if (lane == 0) s_part[warp] = acc;
         __syncthreads();
         if (tid == 0) {
+            if constexpr (RECT2) {      // kept in shared memory across the wavefront (see there)
+                ia = *reinterpret_cast<volatile int *>(&s_pair[0]);
+                ib = *reinterpret_cast<volatile int *>(&s_pair[1]);
+            }
             double k = 0.0;
             for (int i = 0; i < NW; ++i) k += s_part[i];
             // every cell is a term of K, so a cell that overflowed (fp32 mode: beyond 3e38, which large decay factors reach
             // on deep similar trees) or an inf * 0 shows up here; the host entry points re-evaluate such pairs in fp64
             if (!(fabs(k) <= 1.7976931348623157e308)) atomicAdd(a.nonfinite, 1ull);
             if (a.mode == 0) {
-                a.out[w] = k;
+                a.out[RECT2 ? *reinterpret_cast<volatile long long *>(&s_work[0]) : w] = k;
             } else if (a.mode == 1) {
                 if (a.diag) k = k / sqrt(a.diag[ia] * a.diag[ib]);
                 a.out[(long long)ia * a.ld + ib] = k;
@@ -1417,6 +1703,9 @@ static cudaError_t occupancy_t(pk_ctx *ctx, int nt, int smem, int *blocks) {
 // (4 CTAs of 7 warps), <= 256: 80 (3 CTAs), <= 320: 64 and <= 352: 56 (3 CTAs; 800 tips: 432 Gcells/s against 390 in the 384 tier, 900 tips: 415 against 406),
 // <= 384: 80 (2 CTAs), <= 576: 56 (2 CTAs; 1500 tips: 432 against 378 with one CTA), <= 512: 64 (2 CTAs; one CTA of 128 registers ran 5 %
 // (fp64) / 37 % (fp32) slower at 1300 tips), <= 768: 80, else 64 (one CTA per SM)
+#ifdef PK_DEV_TIER      // developer builds (scripts/dev_sass.sh): one unlabelled fp64 tier only, compiles in seconds
+#define PK_DISPATCH(FN, ...) FN<double, false, PK_DEV_TIER, false, 1>(__VA_ARGS__)
+#else
 #define PK_DISPATCH_NT(FN, TT, CS, DL, ...)                                                     \
     (nt <= 64    ? FN<TT, CS, 64, DL, 1>(__VA_ARGS__)                                              \
      : nt <= 192 ? FN<TT, CS, 192, DL, 1>(__VA_ARGS__)                                           \
@@ -1439,6 +1728,7 @@ static cudaError_t occupancy_t(pk_ctx *ctx, int nt, int smem, int *blocks) {
 #define PK_DISPATCH(FN, ...)                                                                                \
     (prec32 ? (deal ? PK_DISPATCH_CS(FN, float, true, __VA_ARGS__) : PK_DISPATCH_CS(FN, float, false, __VA_ARGS__)) \
             : (deal ? PK_DISPATCH_CS(FN, double, true, __VA_ARGS__) : PK_DISPATCH_CS(FN, double, false, __VA_ARGS__)))
+#endif
 
 static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpArgs args, const pk_params *p) {
     if (fa->ctx != ctx || fb->ctx != ctx) return pk_fail(PK_ERR_INVALID, "forest belongs to another context");
@@ -1586,7 +1876,7 @@ static int launch_dp(pk_ctx *ctx, const pk_forest *fa, const pk_forest *fb, DpAr
         if (PK_OVERRUN)
             for (size_t g = 0; g < fa->max_gcnt.size(); ++g) slack = std::max<long long>(slack, std::max(fa->max_gcnt[g], fb->max_gcnt[g]));
         args.slab_elems = ((((maxM + slack) * (long long)w) + 255) & ~255ll) / (long long)w;
-        if (PK_PACKQ && stg != 0 && args.slab_elems >= (1ll << 24))
+        if (PK_PACKQ && stg != 0 && args.slab_elems + PK_XOFF >= (1ll << 24))
             return pk_fail(PK_ERR_INVALID, "internal: staged pair with more than 2^24 stored cells");
         if (args.slab_elems >= (1ll << 31))
             return pk_fail(PK_ERR_INVALID, "tree pair too large: " + std::to_string(args.slab_elems) + " stored cells exceed the 32-bit cell index");
