@@ -127,8 +127,8 @@ __device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity) {
 // 16 j + (l & 15)): a 64-bit LDS is served per half-warp, so every lookup is conflict-free.  The U chains are written
 // stage by stage so the scheduler interleaves them.
 #define PK_EXP_TAB 64
-#ifndef PK_TAB_VOLATILE
-#define PK_TAB_VOLATILE 0
+#ifndef PK_TAB_MAD
+#define PK_TAB_MAD 1
 #endif
 #define PK_EXP_REP 16
 __constant__ double pk_poly[4] = {-0x1.62e42fefa2417p-7, 0x1.ebfbdff82bb76p-15, -0x1.c6b0b9214b9aep-23,
@@ -165,8 +165,10 @@ __device__ __forceinline__ void pk_gauss(const double (&E)[U], double (&out)[U],
         const int k = __double2loint(t[u]);
         unsigned lo;
         int hi;
-#if PK_TAB_VOLATILE      // volatile: stays behind the child-cell gathers issued before the Gaussians (volatile asms keep their order)
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(gk.tab_addr + ((k & (PK_EXP_TAB - 1)) << 7)));
+#if PK_TAB_MAD           // entry address as AND + multiply-add (LOP3, IMAD) instead of the compiler's SHL, LOP3, IADD
+        uint32_t ta;
+        asm("{\n\t.reg .u32 t;\n\tand.b32 t, %1, 63;\n\tmad.lo.u32 %0, t, 128, %2;\n\t}" : "=r"(ta) : "r"(k), "r"(gk.tab_addr));
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(ta));
 #else
         asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(gk.tab_addr + ((k & (PK_EXP_TAB - 1)) << 7)));
 #endif
@@ -466,6 +468,9 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
 #ifndef PK_R2_FENCE
 #define PK_R2_FENCE 0
 #endif
+#ifndef PK_R2_ROT
+#define PK_R2_ROT 1
+#endif
 #define PK_XOFF 16384          // >= the largest rank of a node in its (class, parent code) group; offsets stay below 2^24
 __device__ __forceinline__ void lds_f64x2(uint32_t a, double &x, double &y) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
@@ -526,6 +531,55 @@ __device__ __forceinline__ double pk_rect2(uint32_t ra, int rows, int jb, double
     double f0[U], f1[U];                                              // part: the thread's running sum over the pair, passed through
     const uint32_t rend = ra + 32u * (uint32_t)(rows & ~(U - 1));     // first record after the full groups
     const uint32_t rlast = rend - 32u * U;                            // the last full group (prefetch clamp)
+#if PK_R2_ROT
+    // Rotated software pipeline: the Gaussians of a group are computed while its child cells are in flight -- also those of
+    // the first group of the rectangle (the exposed round trip of every rectangle's head) --, and the loop needs no prefetch
+    // clamp: it runs up to the last full group, which is finished behind it.
+#define PK2_GATHER(at)                                           \
+    if (G0 || G1) {                                              \
+        _Pragma("unroll") for (int u = 0; u < U; ++u) {          \
+            const int2 q = lds_i32x2((at) + 32u * u + 16);       \
+            if (G0) f0[u] = PK2_G0(q.x);                         \
+            if (G1) f1[u] = PK2_G1(q.y);                         \
+        }                                                        \
+    }
+#define PK2_GAUSS(at)                                            \
+    {                                                            \
+        double x[U];                                             \
+        _Pragma("unroll") for (int u = 0; u < U; ++u) {          \
+            double a0, a1;                                       \
+            lds_f64x2((at) + 32u * u, a0, a1);                   \
+            const double d0 = a0 - b0, d1 = a1 - b1;             \
+            x[u] = fma(d1, d1, d0 * d0);                         \
+        }                                                        \
+        pk_gauss<U>(x, ev, gk);                                  \
+    }
+#define PK2_FINISH(at)                                           \
+    _Pragma("unroll") for (int u = 0; u < U; ++u) {              \
+        const int sw = lds_i32((at) + 32u * u + 24);             \
+        if (((sw ^ ptag) & PK_QMASK) == 0) stg_cell(bj, sw, fma(ev[u], g[u], sigma));   \
+        part = fma(ev[u], g[u], part);                           \
+    }
+    if (ra != rend) {
+        double ev[U], g[U];
+        PK2_GATHER(ra)
+        PK2_GAUSS(ra)
+        for (; ra != rlast; ra += 32u * U) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) g[u] = G0 ? (G1 ? f0[u] * f1[u] : f0[u] * cf) : (G1 ? f1[u] * cf : cf);
+            PK2_GATHER(ra + 32u * U)
+            PK2_FINISH(ra)
+            PK2_GAUSS(ra + 32u * U)
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) g[u] = G0 ? (G1 ? f0[u] * f1[u] : f0[u] * cf) : (G1 ? f1[u] * cf : cf);
+        PK2_FINISH(ra)
+        ra += 32u * U;
+    }
+#undef PK2_GATHER
+#undef PK2_GAUSS
+#undef PK2_FINISH
+#else
     if ((G0 || G1) && ra != rend) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -564,6 +618,7 @@ __device__ __forceinline__ double pk_rect2(uint32_t ra, int rows, int jb, double
             part = fma(ev[u], g[u], part);
         }
     }
+#endif
     const int rem = rows & (U - 1);
     if (U > 1 && rem > 0) {
         if (G0 || G1) {
