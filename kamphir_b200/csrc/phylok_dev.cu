@@ -127,6 +127,9 @@ __device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity) {
 // 16 j + (l & 15)): a 64-bit LDS is served per half-warp, so every lookup is conflict-free.  The U chains are written
 // stage by stage so the scheduler interleaves them.
 #define PK_EXP_TAB 64
+#ifndef PK_WHATIF
+#define PK_WHATIF 0      // timing experiments (wrong results), never set in a shipped build
+#endif
 #ifndef PK_TAB_MAD
 #define PK_TAB_MAD 1
 #endif
@@ -168,6 +171,7 @@ __device__ __forceinline__ void pk_gauss(const double (&E)[U], double (&out)[U],
 #if PK_TAB_MAD           // entry address as AND + multiply-add (LOP3, IMAD) instead of the compiler's SHL, LOP3, IADD
         uint32_t ta;
         asm("{\n\t.reg .u32 t;\n\tand.b32 t, %1, 63;\n\tmad.lo.u32 %0, t, 128, %2;\n\t}" : "=r"(ta) : "r"(k), "r"(gk.tab_addr));
+        if (PK_WHATIF & 4) { asm("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(ta)); lo = 0; } else
         asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(ta));
 #else
         asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(gk.tab_addr + ((k & (PK_EXP_TAB - 1)) << 7)));
@@ -523,8 +527,16 @@ __device__ __forceinline__ double pk_rect2(uint32_t ra, int rows, int jb, double
     if (G0) asm volatile("" : "+l"(bk0), "+r"(alt0));
     if (G1) asm volatile("" : "+l"(bk1), "+r"(alt1));
     asm volatile("" : "+l"(bj));
+#if PK_WHATIF & 8      // timing experiment only (wrong results): no gathers at all
+#define PK2_G0(w) (double)(w)
+#define PK2_G1(w) (double)(w)
+#elif PK_WHATIF & 1    // timing experiment only (wrong results): mismatching lanes skip the load
+#define PK2_G0(w) ((((w) ^ alt0) & PK_QMASK) == 0 ? ldg_cell(bk0, (w)) : f0[u])
+#define PK2_G1(w) ((((w) ^ alt1) & PK_QMASK) == 0 ? ldg_cell(bk1, (w)) : f1[u])
+#else
 #define PK2_G0(w) ldg_cell(bk0, (((w) ^ alt0) & PK_QMASK) == 0 ? (w) : alt0)
 #define PK2_G1(w) ldg_cell(bk1, (((w) ^ alt1) & PK_QMASK) == 0 ? (w) : alt1)
+#endif
     double cf = 1.0;                                                       // factor of the slots that are tips in every row
     if (!G0) cf = tag0 == 0 ? tipf : 1.0;
     if (!G1) cf *= tag1 == 0 ? tipf : 1.0;
@@ -548,6 +560,7 @@ __device__ __forceinline__ double pk_rect2(uint32_t ra, int rows, int jb, double
         double x[U];                                             \
         _Pragma("unroll") for (int u = 0; u < U; ++u) {          \
             double a0, a1;                                       \
+            if (PK_WHATIF & 2) { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a0) : "r"((at) + 32u * u)); a1 = a0; } else \
             lds_f64x2((at) + 32u * u, a0, a1);                   \
             const double d0 = a0 - b0, d1 = a1 - b1;             \
             x[u] = fma(d1, d1, d0 * d0);                         \
@@ -1006,7 +1019,7 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
                         }
                     }
                     const int fl = lds_i32(dp + 20);
-                    if (rows > 0 && (fl & 256)) __syncthreads();      // end of a level: its cells are final before the next one reads
+                    if (!(PK_WHATIF & 16) && rows > 0 && (fl & 256)) __syncthreads();      // end of a level: its cells are final before the next one reads
                     if (fl & 2048) break;
                 }
             }
