@@ -38,6 +38,7 @@
 #include <string>
 #include <thread>
 #include <tuple>
+#include <type_traits>
 #include <vector>
 
 #include "phylok_internal.h"
@@ -467,7 +468,7 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
 //      store         :  bj = slab + 8 * (column - tag), word + column - tag = the stored cell: LOP3, IMAD.WIDE, STG
 // ---------------------------------------------------------------------------------------------------
 #ifndef PK_RECT2
-#define PK_RECT2 1
+#define PK_RECT2 2      // 0: off, 1: unlabelled fp64 kernels only, 2: every kernel with staged tree parts and C in HBM slabs
 #endif
 #ifndef PK_R2_FENCE
 #define PK_R2_FENCE 0
@@ -489,64 +490,87 @@ __device__ __forceinline__ int2 lds_i32x2(uint32_t a) {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
     return v;
 }
-__device__ __forceinline__ unsigned long long cell_addr(unsigned long long b, int idx) {     // one IMAD.WIDE.U32
-    return b + (unsigned long long)(unsigned)idx * 8ull;
-}
-__device__ __forceinline__ double ldg_cell(unsigned long long b, int idx) {
-    double v;
-    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(cell_addr(b, idx)));
+__device__ __forceinline__ int4 lds_i32x4(uint32_t a) {
+    int4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
-__device__ __forceinline__ void stg_cell(unsigned long long b, int idx, double v) {
-    asm volatile("st.global.f64 [%0], %1;" ::"l"(cell_addr(b, idx)), "d"(v) : "memory");
+template <typename T>
+__device__ __forceinline__ T lds_real(uint32_t a) {
+    T v;
+    if (sizeof(T) == 8) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(*reinterpret_cast<double *>(&v)) : "r"(a));
+    else asm volatile("ld.shared.f32 %0, [%1];" : "=f"(*reinterpret_cast<float *>(&v)) : "r"(a));
+    return v;
 }
-template <bool G0, bool G1, int U>
-__device__ __forceinline__ double pk_rect2(uint32_t ra, int rows, int jb, double b0, double b1, int cb0, int cb1, int pcode,
-                                           unsigned long long base, const GaussK<double> &gk_in, double sigma, double tipf, double part) {
+template <typename T>
+__device__ __forceinline__ unsigned long long cell_addr(unsigned long long b, int idx) {     // one IMAD.WIDE.U32
+    return b + (unsigned long long)(unsigned)idx * (unsigned long long)sizeof(T);
+}
+template <typename T>
+__device__ __forceinline__ T ldg_cell(unsigned long long b, int idx) {
+    T v;
+    if (sizeof(T) == 8) asm volatile("ld.global.f64 %0, [%1];" : "=d"(*reinterpret_cast<double *>(&v)) : "l"(cell_addr<T>(b, idx)));
+    else asm volatile("ld.global.f32 %0, [%1];" : "=f"(*reinterpret_cast<float *>(&v)) : "l"(cell_addr<T>(b, idx)));
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ void stg_cell(unsigned long long b, int idx, T v) {
+    if (sizeof(T) == 8) asm volatile("st.global.f64 [%0], %1;" ::"l"(cell_addr<T>(b, idx)), "d"(*reinterpret_cast<double *>(&v)) : "memory");
+    else asm volatile("st.global.f32 [%0], %1;" ::"l"(cell_addr<T>(b, idx)), "f"(*reinterpret_cast<float *>(&v)) : "memory");
+}
 #ifndef PK_R2_SIGMA_REG
 #define PK_R2_SIGMA_REG 1
 #endif
+// WIDEP: parent codes beyond 127 are possible (labelled trees with 63 or 64 classes): the store test compares the whole top byte
+template <typename T, bool G0, bool G1, int U, bool WIDEP>
+__device__ __forceinline__ double pk_rect2(uint32_t ra, int rows, int jb, T b0, T b1, int cb0, int cb1, int pcode,
+                                           unsigned long long base, const GaussK<T> &gk_in, T sigma, T tipf, double acc) {
+    constexpr long long W = (long long)sizeof(T);
     const int tag0 = (int)((unsigned)cb0 & 0xff000000u), tag1 = (int)((unsigned)cb1 & 0xff000000u);
     const int rank0 = cb0 & 0xffffff, rank1 = cb1 & 0xffffff;
-    unsigned long long bk0 = base + (unsigned long long)((long long)(rank0 - tag0) * 8);
-    unsigned long long bk1 = base + (unsigned long long)((long long)(rank1 - tag1) * 8);
+    unsigned long long bk0 = base + (unsigned long long)((long long)(rank0 - tag0) * W);
+    unsigned long long bk1 = base + (unsigned long long)((long long)(rank1 - tag1) * W);
     int alt0 = tag0 + (PK_XOFF + 1 - rank0), alt1 = tag1 + (PK_XOFF + 1 - rank1);
-    const int ptag = pcode << 24;
-    unsigned long long bj = base + (unsigned long long)((long long)(jb - ptag) * 8);
+    const unsigned ptag = (unsigned)pcode << 24;
+    constexpr unsigned PMASK = WIDEP ? 0xff000000u : (unsigned)PK_QMASK;
+    unsigned long long bj = base + (unsigned long long)(((long long)jb - (long long)ptag) * W);
+    GaussK<T> gk = gk_in;
 #if PK_R2_SIGMA_REG
-    // sigma and the two highest polynomial coefficients stay in register pairs: read from shared memory with volatile loads,
-    // which ptxas cannot repeat (it otherwise re-reads them from the constant bank in every iteration)
-    GaussK<double> gk = gk_in;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(sigma) : "r"(gk.extra_addr));
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(gk.c3), "=d"(gk.c4) : "r"(gk.extra_addr + 16u));
-    gk.regc = true;
-#else
-    const GaussK<double> &gk = gk_in;
+    // fp64: sigma and the two highest polynomial coefficients stay in register pairs: read from shared memory with volatile
+    // loads, which ptxas cannot repeat (it otherwise re-reads them from the constant bank in every iteration)
+    if constexpr (sizeof(T) == 8) {
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(*reinterpret_cast<double *>(&sigma)) : "r"(gk.extra_addr));
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(gk.c3), "=d"(gk.c4) : "r"(gk.extra_addr + 16u));
+        gk.regc = true;
+    }
 #endif
     // opaque and pinned here: kept in registers as they are, not re-derived per access
     if (G0) asm volatile("" : "+l"(bk0), "+r"(alt0));
     if (G1) asm volatile("" : "+l"(bk1), "+r"(alt1));
     asm volatile("" : "+l"(bj));
 #if PK_WHATIF & 8      // timing experiment only (wrong results): no gathers at all
-#define PK2_G0(w) (double)(w)
-#define PK2_G1(w) (double)(w)
+#define PK2_G0(w) (T)(w)
+#define PK2_G1(w) (T)(w)
 #elif PK_WHATIF & 1    // timing experiment only (wrong results): mismatching lanes skip the load
-#define PK2_G0(w) ((((w) ^ alt0) & PK_QMASK) == 0 ? ldg_cell(bk0, (w)) : f0[u])
-#define PK2_G1(w) ((((w) ^ alt1) & PK_QMASK) == 0 ? ldg_cell(bk1, (w)) : f1[u])
+#define PK2_G0(w) ((((w) ^ alt0) & PK_QMASK) == 0 ? ldg_cell<T>(bk0, (w)) : f0[u])
+#define PK2_G1(w) ((((w) ^ alt1) & PK_QMASK) == 0 ? ldg_cell<T>(bk1, (w)) : f1[u])
 #else
-#define PK2_G0(w) ldg_cell(bk0, (((w) ^ alt0) & PK_QMASK) == 0 ? (w) : alt0)
-#define PK2_G1(w) ldg_cell(bk1, (((w) ^ alt1) & PK_QMASK) == 0 ? (w) : alt1)
+#define PK2_G0(w) ldg_cell<T>(bk0, (((w) ^ alt0) & PK_QMASK) == 0 ? (w) : alt0)
+#define PK2_G1(w) ldg_cell<T>(bk1, (((w) ^ alt1) & PK_QMASK) == 0 ? (w) : alt1)
 #endif
-    double cf = 1.0;                                                       // factor of the slots that are tips in every row
-    if (!G0) cf = tag0 == 0 ? tipf : 1.0;
-    if (!G1) cf *= tag1 == 0 ? tipf : 1.0;
-    double f0[U], f1[U];                                              // part: the thread's running sum over the pair, passed through
+    T cf = (T)1;                                                      // factor of the slots that are tips in every row
+    if (!G0) cf = tag0 == 0 ? tipf : (T)1;
+    if (!G1) cf *= tag1 == 0 ? tipf : (T)1;
+    // fp64: the thread's running sum over the pair is passed through; fp32: an fp32 sum per rectangle, added to it at the end
+    typename std::conditional<sizeof(T) == 8, double, float>::type part = sizeof(T) == 8 ? acc : 0.0;
+    T f0[U], f1[U];
     const uint32_t rend = ra + 32u * (uint32_t)(rows & ~(U - 1));     // first record after the full groups
-    const uint32_t rlast = rend - 32u * U;                            // the last full group (prefetch clamp)
-#if PK_R2_ROT
+    const uint32_t rlast = rend - 32u * U;                            // the last full group
     // Rotated software pipeline: the Gaussians of a group are computed while its child cells are in flight -- also those of
     // the first group of the rectangle (the exposed round trip of every rectangle's head) --, and the loop needs no prefetch
     // clamp: it runs up to the last full group, which is finished behind it.
+    // Row record: fp64 {a0, a1 | off0, off1, store word, -}; fp32 {a0, a1, store word, - | off0, off1, -, -} (one LDS.128
+    // brings the lengths and the store word)
 #define PK2_GATHER(at)                                           \
     if (G0 || G1) {                                              \
         _Pragma("unroll") for (int u = 0; u < U; ++u) {          \
@@ -555,85 +579,49 @@ __device__ __forceinline__ double pk_rect2(uint32_t ra, int rows, int jb, double
             if (G1) f1[u] = PK2_G1(q.y);                         \
         }                                                        \
     }
-#define PK2_GAUSS(at)                                            \
+#define PK2_GAUSS(at, UU, ev_, sw_)                              \
     {                                                            \
-        double x[U];                                             \
-        _Pragma("unroll") for (int u = 0; u < U; ++u) {          \
-            double a0, a1;                                       \
-            if (PK_WHATIF & 2) { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a0) : "r"((at) + 32u * u)); a1 = a0; } else \
-            lds_f64x2((at) + 32u * u, a0, a1);                   \
-            const double d0 = a0 - b0, d1 = a1 - b1;             \
+        T x[UU];                                                 \
+        _Pragma("unroll") for (int u = 0; u < UU; ++u) {         \
+            T a0, a1;                                            \
+            if constexpr (sizeof(T) == 8) {                      \
+                lds_f64x2((at) + 32u * u, *reinterpret_cast<double *>(&a0), *reinterpret_cast<double *>(&a1));   \
+            } else {                                             \
+                const int4 h = lds_i32x4((at) + 32u * u);        \
+                a0 = (T)__int_as_float(h.x);                     \
+                a1 = (T)__int_as_float(h.y);                     \
+                sw_[u] = h.z;                                    \
+            }                                                    \
+            const T d0 = a0 - b0, d1 = a1 - b1;                  \
             x[u] = fma(d1, d1, d0 * d0);                         \
         }                                                        \
-        pk_gauss<U>(x, ev, gk);                                  \
+        pk_gauss<UU>(x, ev_, gk);                                \
     }
-#define PK2_FINISH(at)                                           \
-    _Pragma("unroll") for (int u = 0; u < U; ++u) {              \
-        const int sw = lds_i32((at) + 32u * u + 24);             \
-        if (((sw ^ ptag) & PK_QMASK) == 0) stg_cell(bj, sw, fma(ev[u], g[u], sigma));   \
-        part = fma(ev[u], g[u], part);                           \
+#define PK2_FINISH(at, UU, ev_, g_, sw_)                         \
+    _Pragma("unroll") for (int u = 0; u < UU; ++u) {             \
+        const int sw = sizeof(T) == 8 ? lds_i32((at) + 32u * u + 24) : sw_[u];      \
+        if ((((unsigned)sw ^ ptag) & PMASK) == 0) stg_cell<T>(bj, sw, fma(ev_[u], g_[u], sigma));   \
+        part = fma(ev_[u], g_[u], part);                         \
     }
+#define PK2_PROD(g_, UU)                                         \
+    _Pragma("unroll") for (int u = 0; u < UU; ++u) g_[u] = G0 ? (G1 ? f0[u] * f1[u] : f0[u] * cf) : (G1 ? f1[u] * cf : cf);
     if (ra != rend) {
-        double ev[U], g[U];
+        T ev[U], g[U];
+        int sw4[U];
         PK2_GATHER(ra)
-        PK2_GAUSS(ra)
+        PK2_GAUSS(ra, U, ev, sw4)
         for (; ra != rlast; ra += 32u * U) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) g[u] = G0 ? (G1 ? f0[u] * f1[u] : f0[u] * cf) : (G1 ? f1[u] * cf : cf);
+            PK2_PROD(g, U)
             PK2_GATHER(ra + 32u * U)
-            PK2_FINISH(ra)
-            PK2_GAUSS(ra + 32u * U)
+            PK2_FINISH(ra, U, ev, g, sw4)
+            PK2_GAUSS(ra + 32u * U, U, ev, sw4)
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) g[u] = G0 ? (G1 ? f0[u] * f1[u] : f0[u] * cf) : (G1 ? f1[u] * cf : cf);
-        PK2_FINISH(ra)
+        PK2_PROD(g, U)
+        PK2_FINISH(ra, U, ev, g, sw4)
         ra += 32u * U;
     }
-#undef PK2_GATHER
-#undef PK2_GAUSS
-#undef PK2_FINISH
-#else
-    if ((G0 || G1) && ra != rend) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int2 q = lds_i32x2(ra + 32u * u + 16);
-            if (G0) f0[u] = PK2_G0(q.x);
-            if (G1) f1[u] = PK2_G1(q.y);
-        }
-    }
-    for (; ra != rend; ra += 32u * U) {
-        double x[U], ev[U], g[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            double a0, a1;
-            lds_f64x2(ra + 32u * u, a0, a1);
-            const double d0 = a0 - b0, d1 = a1 - b1;
-            x[u] = fma(d1, d1, d0 * d0);
-            g[u] = G0 ? (G1 ? f0[u] * f1[u] : f0[u] * cf) : (G1 ? f1[u] * cf : cf);
-        }
-        if (G0 || G1) {      // the next group's gathers before this group's Gaussians (the last group re-reads itself)
-            const uint32_t np = min(ra + 32u * U, rlast);
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int2 q = lds_i32x2(np + 32u * u + 16);
-                if (G0) f0[u] = PK2_G0(q.x);
-                if (G1) f1[u] = PK2_G1(q.y);
-            }
-#if PK_R2_FENCE      // memory operations do not cross a warp barrier: the gathers stay in front of the Gaussians (ptxas otherwise sinks
-            __syncwarp(__activemask());      // them to the end of the loop body, a dozen instructions before their first use)
-#endif
-        }
-        pk_gauss<U>(x, ev, gk);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int sw = lds_i32(ra + 32u * u + 24);                 // store offset | parent code << 24
-            if (((sw ^ ptag) & PK_QMASK) == 0) stg_cell(bj, sw, fma(ev[u], g[u], sigma));
-            part = fma(ev[u], g[u], part);
-        }
-    }
-#endif
     const int rem = rows & (U - 1);
-    if (U > 1 && rem > 0) {
+    if (U > 1 && rem > 0) {       // the last 1 .. U - 1 rows: all their gathers first, then one row at a time
         if (G0 || G1) {
 #pragma unroll
             for (int u = 0; u < U - 1; ++u) {
@@ -647,21 +635,23 @@ __device__ __forceinline__ double pk_rect2(uint32_t ra, int rows, int jb, double
 #pragma unroll
         for (int u = 0; u < U - 1; ++u) {
             if (u < rem) {
-                double a0, a1;
-                lds_f64x2(ra + 32u * u, a0, a1);
-                const double d0 = a0 - b0, d1 = a1 - b1;
-                double x1[1] = {fma(d1, d1, d0 * d0)}, e1[1];
-                pk_gauss<1>(x1, e1, gk);
-                const double g = G0 ? (G1 ? f0[u] * f1[u] : f0[u] * cf) : (G1 ? f1[u] * cf : cf);
-                const int sw = lds_i32(ra + 32u * u + 24);
-                if (((sw ^ ptag) & PK_QMASK) == 0) stg_cell(bj, sw, fma(e1[0], g, sigma));
-                part = fma(e1[0], g, part);
+                T e1[1], g1[1];
+                int s1[1];
+                const uint32_t rr = ra + 32u * u;      // (the macros have a loop variable u of their own)
+                PK2_GAUSS(rr, 1, e1, s1)
+                g1[0] = G0 ? (G1 ? f0[u] * f1[u] : f0[u] * cf) : (G1 ? f1[u] * cf : cf);
+                PK2_FINISH(rr, 1, e1, g1, s1)
             }
         }
     }
-    return part;
+#undef PK2_GATHER
+#undef PK2_GAUSS
+#undef PK2_FINISH
+#undef PK2_PROD
 #undef PK2_G0
 #undef PK2_G1
+    if constexpr (sizeof(T) == 8) return part;
+    else return acc + (double)part;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -745,7 +735,7 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
     // 192-thread tier (200-550 tips: 468 against 460 Gcells/s at 500 tips, 348 against 342 at 200), the 320-thread tier
     // (800 tips: 442 against 425) and the 384-thread one (1000 tips: 434 against 432).  fp32 (788 against 805 at 500 tips),
     // the 64-thread tier, the big CTAs (2000 tips: 422 against 437) and the labelled variant lose with it.
-    constexpr bool RECT2 = PK_RECT2 != 0 && sizeof(T) == 8 && !CSMEM && !DEAL && STG == 1;      // pk_rect2 (see there)
+    constexpr bool RECT2 = PK_RECT2 != 0 && !CSMEM && STG == 1 && (PK_RECT2 == 2 || (sizeof(T) == 8 && !DEAL));      // pk_rect2 (see there)
     constexpr int XO = RECT2 ? PK_XOFF : 0;                    // index of the first cell
     constexpr bool PQ = RECT2 || (PK_PACKQ != 0 && STG != 0 &&
                         (PK_PACKQ == 2 || (sizeof(T) == 8 && !DEAL && (BOUND == 192 || BOUND == 320 || BOUND == 384))));
@@ -788,14 +778,6 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
     gk.extra_addr = smem_u32(s_tab) + (sizeof(T) == 8 ? PK_EXP_TAB * PK_EXP_REP * 8u : 0u);
     gk.regc = false;
     gk.c3 = gk.c4 = 0.0;
-    GaussK<double> gk2;                                        // pk_rect2 is fp64 only (the copy is dead code elsewhere)
-    gk2.tab_addr = gk.tab_addr;
-    gk2.clamp_hi = gk.clamp_hi;
-    gk2.lambda = a.lambda;
-    gk2.neg_inv_tau = a.neg_inv_tau;
-    gk2.extra_addr = gk.extra_addr;
-    gk2.regc = false;
-    gk2.c3 = gk2.c4 = 0.0;
 
     if (RECT2 && tid == 0) {      // pk_rect2 kernels keep per-CTA state in shared memory instead of registers (see the wavefront)
         s_state[0] = 0;           // mbarrier parity of the next staging
@@ -862,7 +844,7 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
                 parity ^= 1;
             }
         }
-        if (OVRQ && !CSMEM && tid < PK_PAD_RECORDS) {     // never-matching records after the last row (see PK_OVERRUN)
+        if (OVRQ && !CSMEM && !RECT2 && tid < PK_PAD_RECORDS) {     // never-matching records after the last row (see PK_OVERRUN)
             int4 *padrec = reinterpret_cast<int4 *>(sA + bytesR) + 2 * tid;
             padrec[0] = make_int4(0, 0, 0, 0);
             padrec[1] = PQ ? make_int4((int)0xff000000u, (int)0xff000000u, 0, 0xffff) : make_int4(0, 0, 0, 0xffff);
@@ -925,9 +907,9 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
             const int so = rowoff[r] - (gstB[c * npc + p] - clsB[c]);      // + column position in the class = stored cell
             rec->off0 = PQ ? (o0 | ((pk & 0xff) << 24)) : o0;              // PQ: the child's class + 1 in the top byte
             rec->off1 = PQ ? (o1 | ((pk & 0xff00) << 16)) : o1;
-            rec->st_off = RECT2 ? (so | (p << 24)) : so;       // pk_rect2: the parent code rides in the top byte
+            rec->st_off = RECT2 ? (int)((unsigned)so | ((unsigned)p << 24)) : so;       // pk_rect2: the parent code rides in the top byte
             if constexpr (PQ && sizeof(T) == 4) {
-                rec->st2 = so;
+                rec->st2 = RECT2 ? (int)((unsigned)so | ((unsigned)p << 24)) : so;
                 rec->pk2 = pk;
             }
             rec->a0 *= (T)a.bscale;                // lengths in units that make the squared distance the exponent
@@ -956,19 +938,47 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
                 s_pair[1] = ib;
                 s_state[1] = 0;
             }
+            // one column of one rectangle (descriptor at shared-memory address DP): fields r0, rows, wB, colbase, chunk_end, flags, nchunks, address of the first record
+#define PK_COLUMN2(DP, ROWS, JB)                                                                                                    \
+    {                                                                                                                               \
+        const uint32_t col = (uint32_t)(lds_i32((DP) + 12) + (JB));                                                                 \
+        const T b0 = lds_real<T>(sB32 + lds_i32(sB32 + 24) + (uint32_t)sizeof(T) * col);                                            \
+        const T b1 = lds_real<T>(sB32 + lds_i32(sB32 + 28) + (uint32_t)sizeof(T) * col);                                            \
+        const int cb0 = lds_i32(sB32 + lds_i32(sB32 + 32) + 4u * col), cb1 = lds_i32(sB32 + lds_i32(sB32 + 36) + 4u * col);         \
+        const int pc = lds_i32(sB32 + lds_i32(sB32 + 40) + 4u * col);                                                               \
+        const uint32_t ra = (uint32_t)lds_i32((DP) + 28);                                                                           \
+        unsigned long long base;                                                                                                    \
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(base) : "r"(smem_u32(&s_state[2])));                                          \
+        switch (lds_i32((DP) + 20) & (512 | 1024)) {               /* bit 9 / 10: slot 0 / 1 is a tip in every row of the class */ \
+        case 512 | 1024:                                                                                                            \
+            acc = pk_rect2<T, false, false, U, DEAL>(ra, (ROWS), (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);            \
+            break;                                                                                                                  \
+        case 512:                                                                                                                   \
+            acc = pk_rect2<T, false, true, U, DEAL>(ra, (ROWS), (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);             \
+            break;                                                                                                                  \
+        case 1024:                                                                                                                  \
+            acc = pk_rect2<T, true, false, U, DEAL>(ra, (ROWS), (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);             \
+            break;                                                                                                                  \
+        default:                                                                                                                    \
+            acc = pk_rect2<T, true, true, U, DEAL>(ra, (ROWS), (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);              \
+        }                                                                                                                           \
+    }
             for (;;) {
                 __syncthreads();                       // previous batch done with s_desc; patched records, s_state visible
                 const int L0 = *reinterpret_cast<volatile int *>(&s_state[1]);
                 if (L0 >= lds_i32(sA32 + 8)) break;
+                const int ncls_a = lds_i32(sA32 + 4);
+                const int lpb = DEAL ? max(1, PK_DESC_MAX / ncls_a) : PK_DESC_MAX / 3;      // levels per batch; unlabelled: 3 descriptor slots per level
+                const int dstride = DEAL ? ncls_a : 3;
                 {
-                    const int nlev = lds_i32(sA32 + 8), L1 = min(nlev, L0 + PK_DESC_MAX / 3);
+                    const int nlev = lds_i32(sA32 + 8), L1 = min(nlev, L0 + lpb);
                     const uint32_t lvl32 = sA32 + lds_i32(sA32 + 20), rec32 = sA32 + lds_i32(sA32 + 24), cls32 = sB32 + lds_i32(sB32 + 16);
-                    const unsigned tip0 = lds_i32(sA32 + 28), tip1 = lds_i32(sA32 + 36);
-                    const int ncls_a = lds_i32(sA32 + 4);              // unlabelled trees: at most 3 classes, the descriptors of a level take 3 slots
+                    const unsigned long long tip0 = (unsigned)lds_i32(sA32 + 28) | ((unsigned long long)(unsigned)lds_i32(sA32 + 32) << 32);
+                    const unsigned long long tip1 = (unsigned)lds_i32(sA32 + 36) | ((unsigned long long)(unsigned)lds_i32(sA32 + 40) << 32);
                     for (int L = L0 + tid; L < L1; L += NT) {          // one thread per level describes its rectangles
-                        LevelDesc *dst = s_desc + (L - L0) * 3;
-                        int last = -1;
-                        for (int c = 0; c < 3; ++c) {
+                        LevelDesc *dst = s_desc + (L - L0) * dstride;
+                        int last = -1, chunks = 0;
+                        for (int c = 0; c < dstride; ++c) {
                             LevelDesc d;
                             d.r0 = 0; d.rows = 0; d.wB = 0; d.colbase = 0; d.flags = 0; d.nchunks = 0; d.chunk_end = 0; d.pad1 = 0;
                             if (c < ncls_a) {
@@ -978,51 +988,49 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
                                 d.pad1 = (int)(rec32 + 32u * (uint32_t)r0);          // shared-memory address of the first record
                                 if (rows > 0 && wB > 0) {
                                     d.rows = rows;
-                                    d.flags = (((tip0 >> c) & 1u) ? 512 : 0) | (((tip1 >> c) & 1u) ? 1024 : 0);
+                                    d.flags = (((tip0 >> c) & 1ull) ? 512 : 0) | (((tip1 >> c) & 1ull) ? 1024 : 0);
                                     last = c;
+                                    chunks += (wB + 31) >> 5;
                                 }
                             }
-                            if (c == 2 && L == L1 - 1) d.flags |= 2048;      // last descriptor of the batch
+                            d.chunk_end = chunks;
+                            if (c == dstride - 1 && L == L1 - 1) d.flags |= 2048;      // last descriptor of the batch
                             dst[c] = d;
                         }
                         if (last >= 0) dst[last].flags |= 256;
+                        dst[0].nchunks = chunks;
                     }
                 }
                 __syncthreads();
-                if (tid == 0) s_state[1] = L0 + PK_DESC_MAX / 3;       // read again behind the barrier at the loop's head
-                for (uint32_t dp = smem_u32(s_desc);; dp += (uint32_t)sizeof(LevelDesc)) {      // fields: r0, rows, wB, colbase, chunk_end, flags, nchunks, pad1
-                    const int rows = lds_i32(dp + 4);
-                    if (rows > 0) {                    // uniform
-                        for (int jb = tid; jb < lds_i32(dp + 8); jb += NT) {
-                            const uint32_t col = (uint32_t)(lds_i32(dp + 12) + jb);
-                            double b0, b1;
-                            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b0) : "r"(sB32 + lds_i32(sB32 + 24) + 8u * col));
-                            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b1) : "r"(sB32 + lds_i32(sB32 + 28) + 8u * col));
-                            const int cb0 = lds_i32(sB32 + lds_i32(sB32 + 32) + 4u * col), cb1 = lds_i32(sB32 + lds_i32(sB32 + 36) + 4u * col);
-                            const int pc = lds_i32(sB32 + lds_i32(sB32 + 40) + 4u * col);
-                            const uint32_t ra = (uint32_t)lds_i32(dp + 28);
-                            unsigned long long base;
-                            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(base) : "r"(smem_u32(&s_state[2])));
-                            switch (lds_i32(dp + 20) & (512 | 1024)) {               // bit 9 / 10: slot 0 / 1 is a tip in every row of the class
-                            case 512 | 1024:
-                                acc = pk_rect2<false, false, U>(ra, rows, jb, b0, b1, cb0, cb1, pc, base, gk2, a.sigma, a.sigma + a.lambda, acc);
-                                break;
-                            case 512:
-                                acc = pk_rect2<false, true, U>(ra, rows, jb, b0, b1, cb0, cb1, pc, base, gk2, a.sigma, a.sigma + a.lambda, acc);
-                                break;
-                            case 1024:
-                                acc = pk_rect2<true, false, U>(ra, rows, jb, b0, b1, cb0, cb1, pc, base, gk2, a.sigma, a.sigma + a.lambda, acc);
-                                break;
-                            default:
-                                acc = pk_rect2<true, true, U>(ra, rows, jb, b0, b1, cb0, cb1, pc, base, gk2, a.sigma, a.sigma + a.lambda, acc);
-                            }
+                if (tid == 0) s_state[1] = L0 + lpb;       // read again behind the barrier at the loop's head
+                if (DEAL) {
+                    // the 32-column chunks of all rectangles of a level are numbered through and dealt to the warps round-robin
+                    for (uint32_t dl = smem_u32(s_desc);; dl += (uint32_t)dstride * (uint32_t)sizeof(LevelDesc)) {
+                        const int nchunks = lds_i32(dl + 24);
+                        for (int ch = tid >> 5; ch < nchunks; ch += NT >> 5) {
+                            uint32_t dp = dl;
+                            while (ch >= lds_i32(dp + 16)) dp += (uint32_t)sizeof(LevelDesc);      // uniform per warp, at most ncls steps
+                            const int wB = lds_i32(dp + 8);
+                            const int jb = ((ch - (lds_i32(dp + 16) - ((wB + 31) >> 5))) << 5) + (tid & 31);
+                            if (jb < wB) PK_COLUMN2(dp, lds_i32(dp + 4), jb)
                         }
+                        if (nchunks > 0) __syncthreads();    // end of a level: its cells are final before the next one reads
+                        if (lds_i32(dl + (uint32_t)(dstride - 1) * (uint32_t)sizeof(LevelDesc) + 20) & 2048) break;
                     }
-                    const int fl = lds_i32(dp + 20);
-                    if (!(PK_WHATIF & 16) && rows > 0 && (fl & 256)) __syncthreads();      // end of a level: its cells are final before the next one reads
-                    if (fl & 2048) break;
+                } else {
+                    for (uint32_t dp = smem_u32(s_desc);; dp += (uint32_t)sizeof(LevelDesc)) {
+                        const int rows = lds_i32(dp + 4);
+                        if (rows > 0) {                    // uniform
+                            // thread t owns column t; a rectangle wider than the CTA is finished by the first threads taking a second column
+                            for (int jb = tid; jb < lds_i32(dp + 8); jb += NT) PK_COLUMN2(dp, rows, jb)
+                        }
+                        const int fl = lds_i32(dp + 20);
+                        if (!(PK_WHATIF & 16) && rows > 0 && (fl & 256)) __syncthreads();      // end of a level: its cells are final before the next one reads
+                        if (fl & 2048) break;
+                    }
                 }
             }
+#undef PK_COLUMN2
         } else {
         const int lev_per_batch = max(1, PK_DESC_MAX / ncls);
         for (int L0 = 0; L0 < nlevA; L0 += lev_per_batch) {

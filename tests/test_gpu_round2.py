@@ -263,10 +263,10 @@ def test_tree_parts_left_in_global_memory(precision, states):
             g = pk.gram(flats, normalised=False)
         finally:
             ctx.set_option("unstaged", 0)
-        if option == 1 and (precision == 32 or states):
-            assert np.array_equal(unstaged, staged)      # same row walk, same order of summation
-        # the staged unlabelled fp64 kernels walk the rows with pk_rect2 (one running sum per thread instead of one per
-        # rectangle); other CTA shapes (column-global: threads take several columns in turn) sum in another order
+        if option == 1 and precision == 32:
+            assert np.array_equal(unstaged, staged)      # same rows in the same order, one fp32 sum per rectangle in both
+        # the staged fp64 kernels walk the rows with pk_rect2 (one running sum per thread instead of one per rectangle);
+        # other CTA shapes (column-global: threads take several columns in turn) sum in another order
         assert rel(unstaged, staged) <= (1e-12 if precision == 64 else 1e-6)
         assert rel(g, staged) <= (1e-12 if precision == 64 else 1e-6)      # the Gram form evaluates (i, j) once and mirrors it
 
