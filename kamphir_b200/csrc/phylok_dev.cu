@@ -696,15 +696,16 @@ template <typename T, bool CSMEM, int BOUND, bool DEAL, int STG>     // BOUND: u
 #define PK_MINB192_DEAL 4
 #endif
 #ifndef PK_MINB192_F32
-#define PK_MINB192_F32 5
+#define PK_MINB192_F32 6
 #endif
 // resident CTAs per SM the register budget is set for.  <= 64 threads (100-tip trees): shared memory allows 12 (fp64,
-// 80 registers) / 16 (fp32, 64 registers).  <= 192 threads: 5 CTAs of 64 registers (fp64 at 500 tips: 460 Gcells/s
-// against 452 for 4 CTAs of 80 registers, now that a cell takes 10 % fewer instructions; labelled fp64 stays at 4: its
-// chunk-dealing loop spills at 64 registers).
+// 80 registers) / 16 (fp32, 64 registers).  <= 192 threads: fp64 5 CTAs of 64 registers (pk_rect2 at 500 tips: 510 Gcells/s;
+// 4 CTAs of 80 registers with 2 rows in flight 490, with 4 rows 515 at the price of spills); fp32 6 CTAs of 56 registers
+// (902 against 881 with 5 and 814 with 4); labelled fp64 4 CTAs of 80 registers (3 tip states: shared memory allows no
+// more; 2 states would run 5 % faster with 5), labelled fp32 5 of 64 (496 against 462 with 4).
 __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
                                           : BOUND <= 64  ? (sizeof(T) == 4 ? 16 : 12)
-                                          : BOUND <= 192 ? (sizeof(T) == 4 ? PK_MINB192_F32 : DEAL ? PK_MINB192_DEAL : PK_MINB192)
+                                          : BOUND <= 192 ? (sizeof(T) == 4 ? (DEAL ? 5 : PK_MINB192_F32) : DEAL ? PK_MINB192_DEAL : PK_MINB192)
                                           : BOUND <= 224 ? 4 : BOUND <= 256 ? PK_MINB : BOUND <= 352 ? 3 : BOUND <= 384 ? 2 : BOUND <= 512 ? PK_MINB512
                                           : BOUND <= 576 ? 2 : 1))
     pk_dp_kernel(const DpArgs a) {
@@ -1779,8 +1780,14 @@ static cudaError_t occupancy_t(pk_ctx *ctx, int nt, int smem, int *blocks) {
 // (4 CTAs of 7 warps), <= 256: 80 (3 CTAs), <= 320: 64 and <= 352: 56 (3 CTAs; 800 tips: 432 Gcells/s against 390 in the 384 tier, 900 tips: 415 against 406),
 // <= 384: 80 (2 CTAs), <= 576: 56 (2 CTAs; 1500 tips: 432 against 378 with one CTA), <= 512: 64 (2 CTAs; one CTA of 128 registers ran 5 %
 // (fp64) / 37 % (fp32) slower at 1300 tips), <= 768: 80, else 64 (one CTA per SM)
-#ifdef PK_DEV_TIER      // developer builds (scripts/dev_sass.sh): one unlabelled fp64 tier only, compiles in seconds
-#define PK_DISPATCH(FN, ...) FN<double, false, PK_DEV_TIER, false, 1>(__VA_ARGS__)
+#ifdef PK_DEV_TIER      // developer builds (scripts/dev_sass.sh): one kernel only (default: unlabelled fp64), compiles in seconds
+#ifndef PK_DEV_T
+#define PK_DEV_T double
+#endif
+#ifndef PK_DEV_DEAL
+#define PK_DEV_DEAL false
+#endif
+#define PK_DISPATCH(FN, ...) FN<PK_DEV_T, false, PK_DEV_TIER, PK_DEV_DEAL, 1>(__VA_ARGS__)
 #else
 #define PK_DISPATCH_NT(FN, TT, CS, DL, ...)                                                     \
     (nt <= 64    ? FN<TT, CS, 64, DL, 1>(__VA_ARGS__)                                              \

@@ -33,8 +33,8 @@ def main():
                     if best is None or share > best[0]:
                         best = (share, lo, k)
     share, lo, hi = best
-    out = ["# SASS of the hottest loop of %s (Gram of 192 x 500-tip trees, fp64): the two-gather row loop of pk_rect, two rows in flight." % kern[1],
-           "# From the source page of the ncu capture (profiles/r02_dp_kernel_500tips_*): offset in the function, share of all warp-stall samples, warp instructions executed, SASS.",
+    out = ["# SASS of the hottest loop of %s (Gram of 192 x 500-tip trees, fp64): the two-gather row loop, two rows in flight." % kern[1],
+           "# From the source page of the ncu capture (%s): offset in the function, share of all warp-stall samples, warp instructions executed, SASS." % sys.argv[1],
            "# %d instructions per two rows of 32 cells; the loop holds %.1f %% of the kernel's stall samples." % (hi - lo + 1, 100 * share / tot)]
     for k in range(lo, hi + 1):
         out.append("%06x  %5.2f%%  %9s  %s" % (addr[k] - addr[0], 100 * smp[k] / tot, body[k][E], body[k][S].strip()))
