@@ -658,6 +658,40 @@ class PhyloKernel(object):
                     print('%d\t%d\t%f' % (i, j, self.kmat[i, j]))
         self.is_kmat_computed = True
 
+    # -- consumers of the kernel matrix (the uses README.md:3-5 of the reference names: kernel-PCA, kernel-SVM) -----------
+    def normalised_matrix(self):
+        """K[i,j] / sqrt(K[i,i] K[j,j]) of the computed matrix (the normalisation of kamphir.py:300 applied to ``kmat``)."""
+        if not getattr(self, 'is_kmat_computed', False):
+            raise ValueError("compute_matrix() has not run")
+        d = np.sqrt(np.diag(self.kmat))
+        return self.kmat / np.outer(d, d)
+
+    def save_matrix(self, path, normalised=False):
+        """Write the kernel matrix as ``.npy`` (the input format of scikit-learn's ``kernel='precomputed'`` estimators)."""
+        np.save(path, self.normalised_matrix() if normalised else self.kmat)
+
+    def kernel_pca(self, n_components=2, normalised=True):
+        """Kernel principal components of the tree set from the computed matrix: the matrix is double-centred,
+        K_c = (I - 1/N) K (I - 1/N), and tree i gets the coordinates sqrt(w_k) v_k[i] of the ``n_components`` largest
+        eigenpairs (w_k, v_k) of K_c.  Returns (coordinates [N, n_components], fraction of the variance per component).
+        Host-side numpy on the N x N result; the DP work was done by ``compute_matrix`` / ``gram``."""
+        k = self.normalised_matrix() if normalised else np.asarray(self.kmat, dtype=np.float64)
+        n = k.shape[0]
+        if not 1 <= n_components <= n:
+            raise ValueError("n_components must be between 1 and the number of trees")
+        rm = k.mean(axis=0)
+        kc = k - rm[None, :] - rm[:, None] + rm.mean()
+        w, v = np.linalg.eigh((kc + kc.T) * 0.5)
+        order = np.argsort(w)[::-1][:n_components]
+        w_top = np.clip(w[order], 0.0, None)
+        total = np.clip(w, 0.0, None).sum()
+        coords = v[:, order] * np.sqrt(w_top)[None, :]
+        # sign convention: the entry of largest magnitude of every component is positive (eigenvectors have no sign)
+        for c in range(coords.shape[1]):
+            if coords[np.argmax(np.abs(coords[:, c])), c] < 0:
+                coords[:, c] = -coords[:, c]
+        return coords, (w_top / total if total > 0 else np.zeros_like(w_top))
+
 
 _PAIR00 = np.zeros((1, 2), np.int32)
 

@@ -260,3 +260,30 @@ def test_flattened_form_is_cached_on_the_tree_object_until_it_is_prepared_again(
     assert not np.array_equal(f1.export()[3], f2.export()[3])
     nodes = t.get_nonterminals(order="postorder")
     assert f2.export()[3].tolist() == [n.bl for n in nodes]
+
+
+def test_kernel_matrix_consumers(tmp_path):
+    """normalised_matrix / save_matrix / kernel_pca work on a computed matrix (here: filled by the C oracle, no GPU):
+    the component coordinates reproduce the double-centred matrix and are ordered by variance."""
+    from oracle import c_oracle
+    nwk = synth.tree_set(12, 20, 77)
+    flats = [c_oracle.CFlat(po.prep_kamphir(po.read_newick(s))) for s in nwk]
+    pk = PhyloKernel(decayFactor=0.2, gaussFactor=2.0)
+    with pytest.raises(ValueError):
+        pk.normalised_matrix()
+    pk.kmat = np.array([[c_oracle.kernel(a, b, 0.2, 2.0) for b in flats] for a in flats])
+    pk.is_kmat_computed = True
+    kn = pk.normalised_matrix()
+    assert np.allclose(np.diag(kn), 1.0) and np.allclose(kn, kn.T) and kn.max() <= 1.0 + 1e-12
+    pk.save_matrix(tmp_path / "k.npy")
+    pk.save_matrix(tmp_path / "kn.npy", normalised=True)
+    assert np.array_equal(np.load(tmp_path / "k.npy"), pk.kmat) and np.array_equal(np.load(tmp_path / "kn.npy"), kn)
+    coords, frac = pk.kernel_pca(n_components=11)
+    j = np.eye(12) - 1.0 / 12
+    assert np.allclose(coords @ coords.T, j @ kn @ j, atol=1e-10)          # 11 components span the centred matrix
+    assert np.all(np.diff(frac) <= 1e-12) and abs(frac.sum() - 1.0) < 1e-9
+    assert np.allclose(coords.sum(axis=0), 0.0, atol=1e-9)
+    c2, f2 = pk.kernel_pca(2)
+    assert np.allclose(c2, coords[:, :2]) and np.allclose(f2, frac[:2])
+    with pytest.raises(ValueError):
+        pk.kernel_pca(13)

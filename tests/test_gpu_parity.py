@@ -474,6 +474,12 @@ def test_load_trees_from_file_and_compute_matrix(tmp_path):
     orac = [oracle_flat(s) for s in nwk]
     want = np.array([[c_oracle.kernel(a, b, 0.2, 2.0) for b in orac] for a in orac])
     assert pk.is_kmat_computed and rel(pk.kmat, want) < 1e-9
+    d = np.sqrt(np.diag(want))
+    assert rel(pk.normalised_matrix(), want / np.outer(d, d)) < 1e-9
+    pk.save_matrix(tmp_path / "kmat.npy")
+    assert np.array_equal(np.load(tmp_path / "kmat.npy"), pk.kmat)
+    coords, frac = pk.kernel_pca(2)
+    assert coords.shape == (5, 2) and frac[0] >= frac[1] >= 0.0
 
 
 def test_errors_surface_as_python_exceptions():
