@@ -506,15 +506,34 @@ template <typename T>
 __device__ __forceinline__ unsigned long long cell_addr(unsigned long long b, int idx) {     // one IMAD.WIDE.U32
     return b + (unsigned long long)(unsigned)idx * (unsigned long long)sizeof(T);
 }
+#ifdef PK_DEBUG_BOUNDS
+// pk_rect2 addresses cells through per-lane bases, so the check is on the final address: it must lie inside this CTA's slab
+// (the kernel records the slab's bounds and the violation counter per CTA before the first pair)
+__device__ unsigned long long pk_dbg_lo[4096], pk_dbg_hi[4096];
+__device__ unsigned long long *pk_dbg_err[4096];
+template <typename T>
+__device__ __forceinline__ bool pk_dbg_ok(unsigned long long addr) {
+    const unsigned bx = blockIdx.x & 4095u;
+    if (addr >= pk_dbg_lo[bx] && addr + sizeof(T) <= pk_dbg_hi[bx] && addr % sizeof(T) == 0) return true;
+    atomicAdd(pk_dbg_err[bx], 1ull);
+    return false;
+}
+#endif
 template <typename T>
 __device__ __forceinline__ T ldg_cell(unsigned long long b, int idx) {
     T v;
+#ifdef PK_DEBUG_BOUNDS
+    if (!pk_dbg_ok<T>(cell_addr<T>(b, idx))) return (T)1;
+#endif
     if (sizeof(T) == 8) asm volatile("ld.global.f64 %0, [%1];" : "=d"(*reinterpret_cast<double *>(&v)) : "l"(cell_addr<T>(b, idx)));
     else asm volatile("ld.global.f32 %0, [%1];" : "=f"(*reinterpret_cast<float *>(&v)) : "l"(cell_addr<T>(b, idx)));
     return v;
 }
 template <typename T>
 __device__ __forceinline__ void stg_cell(unsigned long long b, int idx, T v) {
+#ifdef PK_DEBUG_BOUNDS
+    if (!pk_dbg_ok<T>(cell_addr<T>(b, idx))) return;
+#endif
     if (sizeof(T) == 8) asm volatile("st.global.f64 [%0], %1;" ::"l"(cell_addr<T>(b, idx)), "d"(*reinterpret_cast<double *>(&v)) : "memory");
     else asm volatile("st.global.f32 [%0], %1;" ::"l"(cell_addr<T>(b, idx)), "f"(*reinterpret_cast<float *>(&v)) : "memory");
 }
@@ -752,6 +771,12 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
 #ifdef PK_DEBUG_BOUNDS
     cells.limit = (unsigned)a.slab_elems;
     cells.err = a.counter + 1;
+    if (threadIdx.x == 0) {      // for pk_rect2 (visible behind the __syncthreads that follows the table fill)
+        const unsigned long long lo = (unsigned long long)(reinterpret_cast<T *>(a.scratch) + slab_off);
+        pk_dbg_lo[blockIdx.x & 4095u] = lo;
+        pk_dbg_hi[blockIdx.x & 4095u] = lo + (unsigned long long)a.slab_elems * sizeof(T);
+        pk_dbg_err[blockIdx.x & 4095u] = a.counter + 1;
+    }
 #endif
     if (tid == 0) mbar_init(&s_bar, 1);
     if (sizeof(T) == 8)
@@ -873,8 +898,13 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
         //      contiguous column group with its own parent code: R cells per pair instead of M.
         if (tid < ncls) s_cntB[tid] = clsB[tid + 1] - clsB[tid];      // the host launches at least as many threads as classes
         if (tid == 0) {
-            cells.st(XO, tipf);      // tip x tip child factor (phyloK2.py:194-196)
-            cells.st(XO + 1, (T)1);  // factor of a child slot whose productions differ (phyloK2.py:191-192)
+            if constexpr (RECT2) {   // (indices start at XO: not through Cells::st, whose debug check counts from 0)
+                stg_cell<T>(cells.base, XO, tipf);
+                stg_cell<T>(cells.base, XO + 1, (T)1);
+            } else {
+                cells.st(XO, tipf);      // tip x tip child factor (phyloK2.py:194-196)
+                cells.st(XO + 1, (T)1);  // factor of a child slot whose productions differ (phyloK2.py:191-192)
+            }
         }
         // row offsets: exclusive scan of the stored row lengths, by warp 0 (32 rows per step, running carry)
         if (warp == 0) {
@@ -1249,8 +1279,7 @@ struct DeviceGuard {
     DeviceGuard guard__((ctx)->device);                                                                     \
     if (guard__.err != cudaSuccess)                                                                         \
         return pk_fail(PK_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(guard__.err));      \
-    int rc = PK_OK;                                                                                         \
-    (void)rc
+    [[maybe_unused]] int rc = PK_OK
 
 extern "C" int pk_device_count(void) {
     int n = 0;
