@@ -2140,8 +2140,13 @@ static int kernel_pairs_impl(pk_ctx *ctx, const pk_tree *const *A, int32_t nA, c
                                             reinterpret_cast<double *>(d + pb_al));
             if (rc == PK_OK) {
                 e = cudaMemcpyAsync(h + pb_al, d + pb_al, ob, cudaMemcpyDeviceToHost, ctx->stream);
+                const double t1 = trace ? now() : 0.0;
                 if (while_running) (*while_running)();
+                const double t2 = trace ? now() : 0.0;
                 if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+                if (trace)
+                    std::fprintf(stderr, "pk_kernel_pairs: queued after %.0f us, host work while the kernel runs %.0f us, wait %.0f us\n",
+                                 1e6 * (t1 - t0), 1e6 * (t2 - t1), 1e6 * (now() - t2));
                 if (e != cudaSuccess) rc = pk_fail(PK_ERR_CUDA, std::string("pk_kernel_pairs: ") + cudaGetErrorString(e));
                 else std::memcpy(out_k, h + pb_al, ob);
             }
@@ -2231,18 +2236,44 @@ extern "C" int pk_score_newick_batch(pk_ctx *ctx, const pk_tree *obs, const char
     static const bool trace = std::getenv("PK_TRACE") != nullptr;      // PK_TRACE=1: per-phase host times on stderr
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = trace ? now() : 0.0;
-    int rc = pk_trees_from_newick_list(sims, lens, nsims, prep_flags, normalize, n_states, nthreads, &trees, &n);
-    if (rc) return rc;
-    const double t1 = trace ? now() : 0.0;
-    std::vector<double> khat((size_t)n), kc;
     const bool use_kcoal = !std::isnan(kadj);
-    // kcoal is host work (sorting the replicates' node heights) that does not depend on the DP: it runs on the worker
-    // pool while the kernel does (after the forest is packed and uploaded, which uses the same pool).  After that nothing
-    // reads the replicates' host trees any more; they are destroyed in the same window, spread over the pool (a tree is
-    // ~16 heap blocks: 116 us on one thread for 100 trees, a seventh of a configs[1] proposal).
+    // kcoal is host work that does not depend on the DP (sorting a replicate's node heights, three dot products with the
+    // target's): the worker that has just flattened a replicate computes it while the tree is in its cache, so it costs
+    // no dispatch of its own (as a separate pass over the pool it was the longest host phase of a small proposal: 150 us
+    // of 600 for 100 x 100-tip replicates).  A failure (a replicate with more internal nodes than the target, kamphir.py:264)
+    // is reported after the DP, as before.
+    std::vector<double> kc;
     int rc_kcoal = PK_OK;
     std::string err_kcoal;
-    bool kcoal_done = false;
+    std::mutex kcoal_lock;
+    std::function<void(size_t, pk_tree &)> post = [&](size_t k, pk_tree &t) {
+        const int r = pk_kcoal(&t, obs, &kc[k]);
+        if (r) {
+            std::lock_guard<std::mutex> lk(kcoal_lock);
+            if (rc_kcoal == PK_OK) {
+                rc_kcoal = r;
+                err_kcoal = std::string(pk_last_error());
+            }
+        }
+    };
+    // ... for small replicates.  Large ones keep the separate pass behind the launch: there the kernel runs long enough to
+    // hide it (256 x 2000 tips: kernel 1.5 ms, sorting the heights 1.3 ms on 16 cores), and in front of the launch it would
+    // not be hidden by anything.  The text length decides (24 KB is a ~700-tip tree; 100 x 500 tips: 75 us more in the
+    // flattening pass against 120 us that stuck out behind the 100 us kernel).
+    size_t text_bytes = 0;
+    for (int32_t s = 0; s < nsims; ++s) text_bytes += lens[s];
+    const bool kcoal_early = use_kcoal && text_bytes <= (size_t)nsims * 24576;
+    if (use_kcoal) {
+        kc.assign((size_t)nsims, std::numeric_limits<double>::quiet_NaN());
+        if ((int32_t)obs->heights.size() == obs->n) pk_tree_sort_heights(obs);      // once, before the workers read them
+    }
+    int rc = pk_trees_from_newick_list_post(sims, lens, nsims, prep_flags, normalize, n_states, nthreads, &trees, &n,
+                                            kcoal_early ? &post : nullptr);
+    if (rc) return rc;
+    const double t1 = trace ? now() : 0.0;
+    std::vector<double> khat((size_t)n);
+    // After the upload nothing reads the replicates' host trees any more; they are destroyed while the kernel runs, spread
+    // over the pool (a tree is ~16 heap blocks: 116 us on one thread for 100 trees).
     auto free_trees = [&]() {
         if (!trees) return;
         const int workers = std::max(1, std::min(std::min(pk_host_threads(), 16), n / 8));
@@ -2253,20 +2284,15 @@ extern "C" int pk_score_newick_batch(pk_ctx *ctx, const pk_tree *obs, const char
         trees = nullptr;
     };
     std::function<void()> overlap = [&]() {
-        if (use_kcoal) {
-            kc.resize((size_t)n);
+        if (use_kcoal && !kcoal_early) {
             rc_kcoal = pk_kcoal_batch(trees, n, obs, kc.data());
             if (rc_kcoal) err_kcoal = pk_last_error();
-            kcoal_done = true;
         }
         free_trees();
     };
     rc = score_batch_impl(ctx, obs, trees, n, params, ref_denom, out_k, out_denom, khat.data(), &overlap);
     const double t2 = trace ? now() : 0.0;
-    if (rc == PK_OK && use_kcoal) {
-        if (!kcoal_done) overlap();
-        if (rc_kcoal) rc = pk_fail(rc_kcoal, err_kcoal);
-    }
+    if (rc == PK_OK && use_kcoal && rc_kcoal) rc = pk_fail(rc_kcoal, (kcoal_early ? "replicate: " : "") + err_kcoal);
     if (rc == PK_OK) {
         double sum = 0.0;
         for (int32_t s = 0; s < n; ++s) {

@@ -893,7 +893,7 @@ extern "C" int pk_tree_from_newick(const char *text, size_t len, int prep_flags,
 // shared by the two bulk entry points: tree k is text_of(k)[ranges[k].first, ranges[k].second)
 static int flatten_many(const std::vector<const char *> &bases, const std::vector<std::pair<size_t, size_t>> &ranges,
                         size_t total_len, int prep_flags, int normalize, int n_states, int nthreads, pk_tree ***out,
-                        int32_t *n_out);
+                        int32_t *n_out, const std::function<void(size_t, pk_tree &)> *post = nullptr);
 
 extern "C" int pk_trees_from_newick(const char *text, size_t len, int prep_flags, int normalize, int n_states,
                                     int nthreads, pk_tree ***out, int32_t *n_out) {
@@ -908,6 +908,12 @@ extern "C" int pk_trees_from_newick(const char *text, size_t len, int prep_flags
 
 extern "C" int pk_trees_from_newick_list(const char *const *texts, const size_t *lens, int32_t n, int prep_flags,
                                          int normalize, int n_states, int nthreads, pk_tree ***out, int32_t *n_out) {
+    return pk_trees_from_newick_list_post(texts, lens, n, prep_flags, normalize, n_states, nthreads, out, n_out, nullptr);
+}
+
+int pk_trees_from_newick_list_post(const char *const *texts, const size_t *lens, int32_t n, int prep_flags, int normalize,
+                                   int n_states, int nthreads, pk_tree ***out, int32_t *n_out,
+                                   const std::function<void(size_t, pk_tree &)> *post) {
     if (!texts || !lens || !out || !n_out) return pk_fail(PK_ERR_INVALID, "null argument");
     *out = nullptr;
     *n_out = 0;
@@ -922,12 +928,12 @@ extern "C" int pk_trees_from_newick_list(const char *const *texts, const size_t 
         ranges[k] = std::make_pair((size_t)0, e);
         total += lens[k];
     }
-    return flatten_many(bases, ranges, total, prep_flags, normalize, n_states, nthreads, out, n_out);
+    return flatten_many(bases, ranges, total, prep_flags, normalize, n_states, nthreads, out, n_out, post);
 }
 
 static int flatten_many(const std::vector<const char *> &bases, const std::vector<std::pair<size_t, size_t>> &ranges,
                         size_t len, int prep_flags, int normalize, int n_states, int nthreads, pk_tree ***out,
-                        int32_t *n_out) {
+                        int32_t *n_out, const std::function<void(size_t, pk_tree &)> *post) {
     const size_t nt = ranges.size();
     pk_tree **arr = new (std::nothrow) pk_tree *[nt + 1]();
     if (!arr) return pk_fail(PK_ERR_NOMEM, "out of memory");
@@ -951,6 +957,7 @@ static int flatten_many(const std::vector<const char *> &bases, const std::vecto
                 arr[k] = new (std::nothrow) pk_tree();
                 if (!arr[k]) { rc = PK_ERR_NOMEM; err = "out of memory"; }
                 else rc = flatten(text + ranges[k].first, sc, prep_flags, normalize, n_states, *arr[k], err);
+                if (rc == PK_OK && post) (*post)(k, *arr[k]);      // per-tree follow-up work on the worker that has the tree in cache
             }
             if (rc != PK_OK) {
                 bool expected = false;
@@ -1075,6 +1082,8 @@ static const std::vector<double> &pk_sorted_heights(const pk_tree *t) {
     });
     return t->heights;
 }
+
+void pk_tree_sort_heights(const pk_tree *t) { pk_sorted_heights(t); }
 
 extern "C" int pk_tree_node_heights(const pk_tree *t, double *heights) {
     if (!t || !heights) return pk_fail(PK_ERR_INVALID, "null argument");

@@ -82,5 +82,12 @@ int pk_host_threads();
 void pk_set_error(const std::string &msg);
 int pk_fail(int code, const std::string &msg);
 
+// pk_trees_from_newick_list with a follow-up per tree, run by the worker thread that flattened it (tree index, tree)
+int pk_trees_from_newick_list_post(const char *const *texts, const size_t *lens, int32_t n, int prep_flags, int normalize,
+                                   int n_states, int nthreads, pk_tree ***out, int32_t *n_out,
+                                   const std::function<void(size_t, pk_tree &)> *post);
+// sorts the node heights of a tree (kcoal's first step) now instead of on first use
+void pk_tree_sort_heights(const pk_tree *t);
+
 // finishes a tree whose post-order arrays (prod/cls/cidx/bl, n, ncls) are filled: levels, kernel order, histograms
 int pk_tree_finish(pk_tree &t, bool levels_known = false);
