@@ -668,8 +668,15 @@ int pk_tree_finish(pk_tree &t, bool levels_known) {
         }
     }
     t.nlev = nlev;
+    // temporaries of this function live per worker thread: a tree set is finished by the same few threads again and again
+    struct FinishScratch {
+        std::vector<int32_t> cnt, pos, parent, cur, nxt, fill;
+        std::vector<uint32_t> keys;
+    };
+    static thread_local FinishScratch fs;
     // counting sort by (class, level); stable in post-order index
-    std::vector<int32_t> cnt((size_t)ncls * nlev + 1, 0);
+    std::vector<int32_t> &cnt = fs.cnt;
+    cnt.assign((size_t)ncls * nlev + 1, 0);
     for (int32_t i = 0; i < n; ++i) cnt[(size_t)t.cls[i] * nlev + t.level[i] + 1]++;
     for (size_t k = 1; k < cnt.size(); ++k) cnt[k] += cnt[k - 1];
     t.lvl.assign((size_t)ncls * (nlev + 1), 0);
@@ -679,9 +686,10 @@ int pk_tree_finish(pk_tree &t, bool levels_known) {
         t.cls_start[c] = cnt[(size_t)c * nlev];
     }
     t.cls_start[ncls] = n;
-    t.order.assign(n, 0);
-    t.rank.assign(n, 0);
-    std::vector<int32_t> pos(cnt.begin(), cnt.end() - 1);
+    t.order.resize(n);
+    t.rank.resize(n);
+    std::vector<int32_t> &pos = fs.pos;
+    pos.assign(cnt.begin(), cnt.end() - 1);
     for (int32_t i = 0; i < n; ++i) {
         int32_t row = pos[(size_t)t.cls[i] * nlev + t.level[i]]++;
         t.order[row] = i;
@@ -690,7 +698,8 @@ int pk_tree_finish(pk_tree &t, bool levels_known) {
     // parent codes and the column order (class, parent code, ancestor path, post-order)
     const int npc = 2 * ncls + 2;
     t.pcode.assign(n, 0);
-    std::vector<int32_t> parent(n, -1);
+    std::vector<int32_t> &parent = fs.parent;
+    parent.assign(n, -1);
     for (int32_t i = 0; i < n; ++i)
         for (int s = 0; s < 2; ++s) {
             int32_t c = t.cidx[2 * (size_t)i + s];
@@ -707,28 +716,36 @@ int pk_tree_finish(pk_tree &t, bool levels_known) {
     // columns gather from one stored row are then (almost) consecutive too: 3.6 sectors per gather instead of 6.8 at
     // 500 tips.  The own parent code plus those of four ancestors are enough (measured: 3.9 sectors with 4 keys, 3.6 with
     // 6 or 40).
-    t.colorder.assign(n, 0);
-    t.krank.assign(n, 0);
+    t.colorder.resize(n);
+    t.krank.resize(n);
     {
-        // least-significant-key-first radix sort, every pass a stable counting sort over at most npc (or ncls * npc)
-        // buckets: parent code of the 4th, 3rd, 2nd ancestor, of the parent, then the (class, parent code) group; ties
-        // keep the post-order
-        std::vector<int32_t> cur(n), nxt(n), cnt;
+        // The four ancestor keys of a node in one word, byte d = parent code of the ancestor d levels above the parent (0 beyond
+        // the root; codes are below 2 * 64 + 2): a parent comes after its children in post-order, so one pass from the root down
+        // builds every word from the parent's, keys(i) = pcode(parent) | keys(parent) << 8.
+        std::vector<uint32_t> &keys = fs.keys;
+        keys.resize(n);
+        for (int32_t i = n - 1; i >= 0; --i) {
+            const int32_t p = parent[i];
+            if (p >= 0 && p <= i) return pk_fail(PK_ERR_INVALID, "child index is not below its parent in post-order");
+            keys[i] = p >= 0 ? ((uint32_t)t.pcode[p] | (keys[p] << 8)) : 0u;
+        }
+        // least-significant-key-first radix sort, every pass a stable counting sort over at most npc buckets: parent code
+        // of the 4th, 3rd, 2nd ancestor, of the parent, then the (class, parent code) group; ties keep the post-order
+        std::vector<int32_t> &cur = fs.cur, &nxt = fs.nxt;
+        cur.resize(n);
+        nxt.resize(n);
         for (int32_t i = 0; i < n; ++i) cur[i] = i;
-        std::vector<uint8_t> key(n);
         for (int d = 3; d >= 0; --d) {
-            for (int32_t i = 0; i < n; ++i) {
-                int32_t v = parent[i];
-                for (int k = 0; k < d && v >= 0; ++k) v = parent[v];
-                key[i] = v >= 0 ? t.pcode[v] : 0;
-            }
+            const int sh = 8 * d;
             cnt.assign((size_t)npc + 1, 0);
-            for (int32_t i = 0; i < n; ++i) cnt[key[i] + 1]++;
+            for (int32_t i = 0; i < n; ++i) cnt[((keys[i] >> sh) & 0xffu) + 1]++;
+            if (cnt[1] == n) continue;                 // every node has key 0 at this depth (shallow tree): order unchanged
             for (int k = 0; k < npc; ++k) cnt[k + 1] += cnt[k];
-            for (int32_t c = 0; c < n; ++c) nxt[cnt[key[cur[c]]]++] = cur[c];
+            for (int32_t c = 0; c < n; ++c) nxt[cnt[(keys[cur[c]] >> sh) & 0xffu]++] = cur[c];
             cur.swap(nxt);
         }
-        std::vector<int32_t> fill(t.gstart.begin(), t.gstart.end() - 1);
+        std::vector<int32_t> &fill = fs.fill;
+        fill.assign(t.gstart.begin(), t.gstart.end() - 1);
         for (int32_t c = 0; c < n; ++c) {
             const int32_t i = cur[c];
             const size_t g = (size_t)t.cls[i] * npc + t.pcode[i];
