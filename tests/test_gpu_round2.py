@@ -323,3 +323,25 @@ def test_repeated_uploads_of_a_tree_set_come_out_of_the_cached_image():
         full.close()
     for r in runners:
         r.close()
+
+
+def test_kcoal_placement_small_and_large_replicates():
+    """pk_score_newick_batch computes kcoal inside the flattening pass for small replicates and behind the launch for large
+    ones (24 KB of text per tree decides): both give the numbers of the object path; a replicate with more internal nodes
+    than the target is an error on either route (IndexError at kamphir.py:264 in the reference)."""
+    from kamphir_b200 import FlatTree, PhyloKernel, synth
+    pk = PhyloKernel(decayFactor=0.2, gaussFactor=2.0)
+    for tips, nrep in ((60, 12), (900, 6)):
+        obs = synth.kingman_newick(tips, 11)
+        sims = [synth.kingman_newick(tips, 500 + i) for i in range(nrep)]
+        assert (max(len(s) for s in sims) < 24576) == (tips == 60)
+        a = pk.score_batch(obs, [x.encode() for x in sims], use_kcoal=True)
+        fl = [FlatTree.from_newick(x) for x in sims]
+        fo = FlatTree.from_newick(obs)
+        want = np.array([t.kcoal(fo) for t in fl])
+        assert np.array_equal(a["kcoal"], want)
+        assert np.allclose(a["score"], a["knorm"] * want, rtol=1e-14, atol=0)
+        bigger = synth.kingman_newick(tips + 5, 999)
+        with pytest.raises(ValueError, match="more internal nodes"):
+            pk.score_batch(obs, [x.encode() for x in sims[:3]] + [bigger.encode()], use_kcoal=True)
+        pk.score_batch(obs, [x.encode() for x in sims[:3]] + [bigger.encode()])      # without kcoal it is a valid replicate
