@@ -476,6 +476,9 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
 #ifndef PK_R2_ROT
 #define PK_R2_ROT 1
 #endif
+#ifndef PK_DESC2
+#define PK_DESC2 1      // unlabelled pk_rect2 kernels: a rectangle's descriptor carries the addresses of its columns' data
+#endif
 #define PK_XOFF 16384          // >= the largest rank of a node in its (class, parent code) group; offsets stay below 2^24
 __device__ __forceinline__ void lds_f64x2(uint32_t a, double &x, double &y) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
@@ -994,6 +997,39 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
             acc = pk_rect2<T, true, true, U, DEAL>(ra, (ROWS), (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);              \
         }                                                                                                                           \
     }
+            // PK_DESC2 (unlabelled trees): the descriptor of a rectangle is {address of its first column's b0, rows, wB, address
+            // of its first column's code0 | b1 - b0 array distance, flags, code array distance, address of the first record}, so a
+            // thread sets up its column with two LDS.128 of the descriptor and five loads of its column's data -- eight loads
+            // less per rectangle than going through the staged headers (~50 rectangles per 500-tip pair)
+            // Where two rows are in flight per lane (measured per tier, fp64 Gcells/s: 192 threads 512 -> 522, 64 threads 229 ->
+            // 234, 200 tips 388 -> 398, 320 threads 465 -> 470, 576 threads 489 -> 492); the tiers with four rows in flight and
+            // 80 registers lose with it (384 threads 511 -> 487, 768 threads 487 -> 469: ptxas' schedule of the larger loop).
+            constexpr bool D2 = PK_DESC2 != 0 && !DEAL && (PK_DESC2 == 2 || U == 2);
+#define PK_COLUMN2D(DP, Q1, JB)                                                                                                      \
+    {                                                                                                                               \
+        const int4 q2 = lds_i32x4((DP) + 16);                       /* {b1 - b0 distance, flags, code distance, first record} */    \
+        const uint32_t ab = (uint32_t)(Q1).x + (uint32_t)sizeof(T) * (uint32_t)(JB), ac = (uint32_t)(Q1).w + 4u * (uint32_t)(JB);   \
+        const T b0 = lds_real<T>(ab);                                                                                               \
+        const T b1 = lds_real<T>(ab + (uint32_t)q2.x);                                                                              \
+        const int cb0 = lds_i32(ac), cb1 = lds_i32(ac + (uint32_t)q2.z);                                                            \
+        const int pc = lds_i32(ac + 2u * (uint32_t)q2.z);                                                                           \
+        const uint32_t ra = (uint32_t)q2.w;                                                                                         \
+        unsigned long long base;                                                                                                    \
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(base) : "r"(smem_u32(&s_state[2])));                                          \
+        switch (q2.y & (512 | 1024)) {                                                                                              \
+        case 512 | 1024:                                                                                                            \
+            acc = pk_rect2<T, false, false, U, DEAL>(ra, (Q1).y, (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);            \
+            break;                                                                                                                  \
+        case 512:                                                                                                                   \
+            acc = pk_rect2<T, false, true, U, DEAL>(ra, (Q1).y, (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);             \
+            break;                                                                                                                  \
+        case 1024:                                                                                                                  \
+            acc = pk_rect2<T, true, false, U, DEAL>(ra, (Q1).y, (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);             \
+            break;                                                                                                                  \
+        default:                                                                                                                    \
+            acc = pk_rect2<T, true, true, U, DEAL>(ra, (Q1).y, (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);              \
+        }                                                                                                                           \
+    }
             for (;;) {
                 __syncthreads();                       // previous batch done with s_desc; patched records, s_state visible
                 const int L0 = *reinterpret_cast<volatile int *>(&s_state[1]);
@@ -1017,6 +1053,12 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
                                 const int wB = s_cntB[c];
                                 d.r0 = r0; d.wB = wB; d.colbase = lds_i32(cls32 + 4 * c);
                                 d.pad1 = (int)(rec32 + 32u * (uint32_t)r0);          // shared-memory address of the first record
+                                if constexpr (D2) {      // (the code0, code1 and parent-code arrays are equally long)
+                                    const int colbase = d.colbase;
+                                    d.r0 = (int)(sB32 + (uint32_t)lds_i32(sB32 + 24) + (uint32_t)sizeof(T) * (uint32_t)colbase);
+                                    d.colbase = (int)(sB32 + (uint32_t)lds_i32(sB32 + 32) + 4u * (uint32_t)colbase);
+                                    chunks = 0;
+                                }
                                 if (rows > 0 && wB > 0) {
                                     d.rows = rows;
                                     d.flags = (((tip0 >> c) & 1ull) ? 512 : 0) | (((tip1 >> c) & 1ull) ? 1024 : 0);
@@ -1026,10 +1068,14 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
                             }
                             d.chunk_end = chunks;
                             if (c == dstride - 1 && L == L1 - 1) d.flags |= 2048;      // last descriptor of the batch
+                            if constexpr (D2) {
+                                d.chunk_end = lds_i32(sB32 + 28) - lds_i32(sB32 + 24);     // b0 array -> b1 array
+                                d.nchunks = lds_i32(sB32 + 36) - lds_i32(sB32 + 32);       // code0 -> code1 -> parent codes
+                            }
                             dst[c] = d;
                         }
                         if (last >= 0) dst[last].flags |= 256;
-                        dst[0].nchunks = chunks;
+                        if constexpr (!D2) dst[0].nchunks = chunks;
                     }
                 }
                 __syncthreads();
@@ -1048,6 +1094,16 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
                         if (nchunks > 0) __syncthreads();    // end of a level: its cells are final before the next one reads
                         if (lds_i32(dl + (uint32_t)(dstride - 1) * (uint32_t)sizeof(LevelDesc) + 20) & 2048) break;
                     }
+                } else if constexpr (D2) {
+                    for (uint32_t dp = smem_u32(s_desc);; dp += (uint32_t)sizeof(LevelDesc)) {
+                        const int4 q1 = lds_i32x4(dp);             // {b0 address, rows, wB, code0 address}
+                        if (q1.y > 0) {                    // uniform
+                            for (int jb = tid; jb < q1.z; jb += NT) PK_COLUMN2D(dp, q1, jb)
+                        }
+                        const int fl = lds_i32(dp + 20);
+                        if (q1.y > 0 && (fl & 256)) __syncthreads();      // end of a level: its cells are final before the next one reads
+                        if (fl & 2048) break;
+                    }
                 } else {
                     for (uint32_t dp = smem_u32(s_desc);; dp += (uint32_t)sizeof(LevelDesc)) {
                         const int rows = lds_i32(dp + 4);
@@ -1062,6 +1118,7 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
                 }
             }
 #undef PK_COLUMN2
+#undef PK_COLUMN2D
         } else {
         const int lev_per_batch = max(1, PK_DESC_MAX / ncls);
         for (int L0 = 0; L0 < nlevA; L0 += lev_per_batch) {
