@@ -544,16 +544,19 @@ __device__ __forceinline__ void stg_cell(unsigned long long b, int idx, T v) {
 #define PK_R2_SIGMA_REG 1
 #endif
 // WIDEP: parent codes beyond 127 are possible (labelled trees with 63 or 64 classes): the store test compares the whole top byte
-template <typename T, bool G0, bool G1, int U, bool WIDEP>
+// CONV: the column's words were converted when the pair was staged (PK_DESC2 kernels): cb0 / cb1 arrive as rank - tag (0 for a
+// tip child, negative otherwise: a tag is at least 2^24, a rank below it) and pcode as the parent code << 24
+template <typename T, bool G0, bool G1, int U, bool WIDEP, bool CONV>
 __device__ __forceinline__ double pk_rect2(uint32_t ra, int rows, int jb, T b0, T b1, int cb0, int cb1, int pcode,
                                            unsigned long long base, const GaussK<T> &gk_in, T sigma, T tipf, double acc) {
     constexpr long long W = (long long)sizeof(T);
-    const int tag0 = (int)((unsigned)cb0 & 0xff000000u), tag1 = (int)((unsigned)cb1 & 0xff000000u);
-    const int rank0 = cb0 & 0xffffff, rank1 = cb1 & 0xffffff;
-    unsigned long long bk0 = base + (unsigned long long)((long long)(rank0 - tag0) * W);
-    unsigned long long bk1 = base + (unsigned long long)((long long)(rank1 - tag1) * W);
-    int alt0 = tag0 + (PK_XOFF + 1 - rank0), alt1 = tag1 + (PK_XOFF + 1 - rank1);
-    const unsigned ptag = (unsigned)pcode << 24;
+    const int d0 = CONV ? cb0 : (cb0 & 0xffffff) - (int)((unsigned)cb0 & 0xff000000u);
+    const int d1 = CONV ? cb1 : (cb1 & 0xffffff) - (int)((unsigned)cb1 & 0xff000000u);
+    const int tag0 = d0, tag1 = d1;      // only ever compared with 0 (tip child)
+    unsigned long long bk0 = base + (unsigned long long)((long long)d0 * W);
+    unsigned long long bk1 = base + (unsigned long long)((long long)d1 * W);
+    int alt0 = (PK_XOFF + 1) - d0, alt1 = (PK_XOFF + 1) - d1;      // = tag + (PK_XOFF + 1 - rank)
+    const unsigned ptag = CONV ? (unsigned)pcode : (unsigned)pcode << 24;
     constexpr unsigned PMASK = WIDEP ? 0xff000000u : (unsigned)PK_QMASK;
     unsigned long long bj = base + (unsigned long long)(((long long)jb - (long long)ptag) * W);
     GaussK<T> gk = gk_in;
@@ -760,6 +763,10 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
     // the 64-thread tier, the big CTAs (2000 tips: 422 against 437) and the labelled variant lose with it.
     constexpr bool RECT2 = PK_RECT2 != 0 && !CSMEM && STG == 1 && (PK_RECT2 == 2 || (sizeof(T) == 8 && !DEAL));      // pk_rect2 (see there)
     constexpr int XO = RECT2 ? PK_XOFF : 0;                    // index of the first cell
+    // descriptors with the column-data addresses, only the live rectangles visited, column words converted per pair (see the
+    // wavefront): in the tiers with two rows in flight, except the 56-register fp64 tier of 576 threads (1500 tips: 490 against
+    // 497 Gcells/s with it)
+    constexpr bool D2 = PK_DESC2 != 0 && RECT2 && !DEAL && (PK_DESC2 == 2 || (U == 2 && !(sizeof(T) == 8 && BOUND == 576)));
     constexpr bool PQ = RECT2 || (PK_PACKQ != 0 && STG != 0 &&
                         (PK_PACKQ == 2 || (sizeof(T) == 8 && !DEAL && (BOUND == 192 || BOUND == 320 || BOUND == 384))));
     unsigned char *const gstage = STG == 1 ? nullptr : a.stage + (size_t)blockIdx.x * (size_t)a.stage_stride;
@@ -955,6 +962,13 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
             for (int c = tid; c < nB; c += NT) {
                 b0w[c] *= (T)a.bscale;
                 b1w[c] *= (T)a.bscale;
+                if constexpr (D2) {      // the column's words as pk_rect2 uses them: rank - tag per child, parent code << 24
+                    int *c0w = const_cast<int *>(codeB0), *c1w = const_cast<int *>(codeB1), *pw = const_cast<int *>(pcB);
+                    const int x0 = c0w[c], x1 = c1w[c];
+                    c0w[c] = (x0 & 0xffffff) - (int)((unsigned)x0 & 0xff000000u);
+                    c1w[c] = (x1 & 0xffffff) - (int)((unsigned)x1 & 0xff000000u);
+                    pw[c] = (int)((unsigned)pw[c] << 24);
+                }
             }
         }
 
@@ -985,26 +999,29 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
         asm volatile("ld.shared.u64 %0, [%1];" : "=l"(base) : "r"(smem_u32(&s_state[2])));                                          \
         switch (lds_i32((DP) + 20) & (512 | 1024)) {               /* bit 9 / 10: slot 0 / 1 is a tip in every row of the class */ \
         case 512 | 1024:                                                                                                            \
-            acc = pk_rect2<T, false, false, U, DEAL>(ra, (ROWS), (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);            \
+            acc = pk_rect2<T, false, false, U, DEAL, false>(ra, (ROWS), (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);            \
             break;                                                                                                                  \
         case 512:                                                                                                                   \
-            acc = pk_rect2<T, false, true, U, DEAL>(ra, (ROWS), (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);             \
+            acc = pk_rect2<T, false, true, U, DEAL, false>(ra, (ROWS), (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);             \
             break;                                                                                                                  \
         case 1024:                                                                                                                  \
-            acc = pk_rect2<T, true, false, U, DEAL>(ra, (ROWS), (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);             \
+            acc = pk_rect2<T, true, false, U, DEAL, false>(ra, (ROWS), (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);             \
             break;                                                                                                                  \
         default:                                                                                                                    \
-            acc = pk_rect2<T, true, true, U, DEAL>(ra, (ROWS), (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);              \
+            acc = pk_rect2<T, true, true, U, DEAL, false>(ra, (ROWS), (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);              \
         }                                                                                                                           \
     }
             // PK_DESC2 (unlabelled trees): the descriptor of a rectangle is {address of its first column's b0, rows, wB, address
             // of its first column's code0 | b1 - b0 array distance, flags, code array distance, address of the first record}, so a
             // thread sets up its column with two LDS.128 of the descriptor and five loads of its column's data -- eight loads
             // less per rectangle than going through the staged headers (~50 rectangles per 500-tip pair)
-            // Where two rows are in flight per lane (measured per tier, fp64 Gcells/s: 192 threads 512 -> 522, 64 threads 229 ->
-            // 234, 200 tips 388 -> 398, 320 threads 465 -> 470, 576 threads 489 -> 492); the tiers with four rows in flight and
-            // 80 registers lose with it (384 threads 511 -> 487, 768 threads 487 -> 469: ptxas' schedule of the larger loop).
-            constexpr bool D2 = PK_DESC2 != 0 && !DEAL && (PK_DESC2 == 2 || U == 2);
+            // Only the live rectangles of a level get a descriptor (the level's last one says how many slots lie between it and
+            // the next level's first), and the column's words are converted once per pair, when it is staged, into what pk_rect2
+            // computes with (rank - tag per child, parent code << 24).
+            // Measured per tier, fp64 Gcells/s: 192 threads (500 tips) 513 -> 529, 64 threads (100 tips) 229 -> 241, 200 tips
+            // 388 -> 408, 320 threads 469 -> 478; fp32 500 tips 901 -> 969, 200 tips 611 -> 677, 1000 tips 862 -> 882.  The
+            // tiers with four rows in flight and 80 registers lose with it (384 threads 511 -> 487, 768 threads 487 -> 469:
+            // ptxas' schedule of the larger loop) and keep the walk through the staged headers.
 #define PK_COLUMN2D(DP, Q1, JB)                                                                                                      \
     {                                                                                                                               \
         const int4 q2 = lds_i32x4((DP) + 16);                       /* {b1 - b0 distance, flags, code distance, first record} */    \
@@ -1018,16 +1035,16 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
         asm volatile("ld.shared.u64 %0, [%1];" : "=l"(base) : "r"(smem_u32(&s_state[2])));                                          \
         switch (q2.y & (512 | 1024)) {                                                                                              \
         case 512 | 1024:                                                                                                            \
-            acc = pk_rect2<T, false, false, U, DEAL>(ra, (Q1).y, (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);            \
+            acc = pk_rect2<T, false, false, U, DEAL, true>(ra, (Q1).y, (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);            \
             break;                                                                                                                  \
         case 512:                                                                                                                   \
-            acc = pk_rect2<T, false, true, U, DEAL>(ra, (Q1).y, (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);             \
+            acc = pk_rect2<T, false, true, U, DEAL, true>(ra, (Q1).y, (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);             \
             break;                                                                                                                  \
         case 1024:                                                                                                                  \
-            acc = pk_rect2<T, true, false, U, DEAL>(ra, (Q1).y, (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);             \
+            acc = pk_rect2<T, true, false, U, DEAL, true>(ra, (Q1).y, (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);             \
             break;                                                                                                                  \
         default:                                                                                                                    \
-            acc = pk_rect2<T, true, true, U, DEAL>(ra, (Q1).y, (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);              \
+            acc = pk_rect2<T, true, true, U, DEAL, true>(ra, (Q1).y, (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);              \
         }                                                                                                                           \
     }
             for (;;) {
@@ -1045,6 +1062,7 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
                     for (int L = L0 + tid; L < L1; L += NT) {          // one thread per level describes its rectangles
                         LevelDesc *dst = s_desc + (L - L0) * dstride;
                         int last = -1, chunks = 0;
+                        int slot = 0;      // D2: the level's non-empty rectangles are written to its first slots
                         for (int c = 0; c < dstride; ++c) {
                             LevelDesc d;
                             d.r0 = 0; d.rows = 0; d.wB = 0; d.colbase = 0; d.flags = 0; d.nchunks = 0; d.chunk_end = 0; d.pad1 = 0;
@@ -1067,15 +1085,33 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
                                 }
                             }
                             d.chunk_end = chunks;
-                            if (c == dstride - 1 && L == L1 - 1) d.flags |= 2048;      // last descriptor of the batch
+                            if (!D2 && c == dstride - 1 && L == L1 - 1) d.flags |= 2048;      // last descriptor of the batch
                             if constexpr (D2) {
                                 d.chunk_end = lds_i32(sB32 + 28) - lds_i32(sB32 + 24);     // b0 array -> b1 array
                                 d.nchunks = lds_i32(sB32 + 36) - lds_i32(sB32 + 32);       // code0 -> code1 -> parent codes
+                                // only the non-empty rectangles are visited: bits 12-13 of the flags = slots to the next
+                                // descriptor (the level's last one leads to the next level's first slot)
+                                if (d.rows > 0) {
+                                    d.flags |= 1 << 12;
+                                    dst[slot++] = d;
+                                }
+                            } else {
+                                dst[c] = d;
                             }
-                            dst[c] = d;
                         }
-                        if (last >= 0) dst[last].flags |= 256;
-                        if constexpr (!D2) dst[0].nchunks = chunks;
+                        if constexpr (D2) {
+                            if (slot == 0) {      // a level without live cells (the column tree lacks the classes of its rows)
+                                LevelDesc d;
+                                d.r0 = 0; d.rows = 0; d.wB = 0; d.colbase = 0; d.flags = 0; d.nchunks = 0; d.chunk_end = 0; d.pad1 = 0;
+                                dst[slot++] = d;
+                            } else {
+                                dst[slot - 1].flags |= 256;
+                            }
+                            dst[slot - 1].flags = (dst[slot - 1].flags & ~(3 << 12)) | ((dstride - (slot - 1)) << 12) | (L == L1 - 1 ? 2048 : 0);
+                        } else {
+                            if (last >= 0) dst[last].flags |= 256;
+                            dst[0].nchunks = chunks;
+                        }
                     }
                 }
                 __syncthreads();
@@ -1095,14 +1131,15 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
                         if (lds_i32(dl + (uint32_t)(dstride - 1) * (uint32_t)sizeof(LevelDesc) + 20) & 2048) break;
                     }
                 } else if constexpr (D2) {
-                    for (uint32_t dp = smem_u32(s_desc);; dp += (uint32_t)sizeof(LevelDesc)) {
+                    for (uint32_t dp = smem_u32(s_desc);;) {
                         const int4 q1 = lds_i32x4(dp);             // {b0 address, rows, wB, code0 address}
                         if (q1.y > 0) {                    // uniform
                             for (int jb = tid; jb < q1.z; jb += NT) PK_COLUMN2D(dp, q1, jb)
                         }
                         const int fl = lds_i32(dp + 20);
-                        if (q1.y > 0 && (fl & 256)) __syncthreads();      // end of a level: its cells are final before the next one reads
+                        if (fl & 256) __syncthreads();      // end of a level: its cells are final before the next one reads
                         if (fl & 2048) break;
+                        dp += (uint32_t)((fl >> 12) & 3) * (uint32_t)sizeof(LevelDesc);
                     }
                 } else {
                     for (uint32_t dp = smem_u32(s_desc);; dp += (uint32_t)sizeof(LevelDesc)) {
