@@ -1085,7 +1085,7 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
                                 }
                             }
                             d.chunk_end = chunks;
-                            if (!D2 && c == dstride - 1 && L == L1 - 1) d.flags |= 2048;      // last descriptor of the batch
+                            if (!D2 && !DEAL && c == dstride - 1 && L == L1 - 1) d.flags |= 2048;      // last descriptor of the batch
                             if constexpr (D2) {
                                 d.chunk_end = lds_i32(sB32 + 28) - lds_i32(sB32 + 24);     // b0 array -> b1 array
                                 d.nchunks = lds_i32(sB32 + 36) - lds_i32(sB32 + 32);       // code0 -> code1 -> parent codes
@@ -1095,9 +1095,22 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
                                     d.flags |= 1 << 12;
                                     dst[slot++] = d;
                                 }
+                            } else if constexpr (DEAL) {
+                                // labelled trees: the live rectangles first, so that a warp looking for the rectangle of its
+                                // chunk steps over no empty descriptors (1 + 2S + S^2 classes, half of them absent from a level)
+                                if (d.rows > 0) dst[slot++] = d;
                             } else {
                                 dst[c] = d;
                             }
+                        }
+                        if constexpr (DEAL) {
+                            for (int k = slot; k < dstride; ++k) {
+                                LevelDesc d;
+                                d.r0 = 0; d.rows = 0; d.wB = 0; d.colbase = 0; d.flags = 0; d.nchunks = 0; d.chunk_end = chunks; d.pad1 = 0;
+                                dst[k] = d;
+                            }
+                            if (L == L1 - 1) dst[dstride - 1].flags |= 2048;      // last descriptor of the batch
+                            last = -1;
                         }
                         if constexpr (D2) {
                             if (slot == 0) {      // a level without live cells (the column tree lacks the classes of its rows)
