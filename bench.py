@@ -656,7 +656,7 @@ def run_ours(args):
         achieved = alg_bytes / (dp_ms_avg / 1e3) / 1e9
         # DRAM traffic of the same kernel from the committed ncu --set full capture, scaled per DP to this launch
         traffic, traffic_src = None, None
-        for rnd in ("r02b", "r02", "r01"):
+        for rnd in ("r02e", "r02d", "r02b", "r02", "r01"):
             try:
                 cap_name = "%s_dram_traffic%s.json" % (rnd, "_fp32" if args.precision == 32 else "")
                 cap = json.load(open(os.path.join(REPO, "profiles", cap_name)))
