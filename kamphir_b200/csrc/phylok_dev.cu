@@ -633,7 +633,11 @@ __device__ __forceinline__ double pk_rect2(uint32_t ra, int rows, int jb, T b0, 
     if (ra != rend) {
         T ev[U], g[U];
         int sw4[U];
+#if PK_WHATIF & 32      // timing experiment only (wrong results): the first group of a rectangle takes no child cells
+        _Pragma("unroll") for (int u = 0; u < U; ++u) { f0[u] = (T)(ra + u); f1[u] = (T)(rows + u); }
+#else
         PK2_GATHER(ra)
+#endif
         PK2_GAUSS(ra, U, ev, sw4)
         for (; ra != rlast; ra += 32u * U) {
             PK2_PROD(g, U)
