@@ -476,6 +476,9 @@ __device__ __forceinline__ T pk_rect(const RowRec<T> *rp, int rows, int jb, T b0
 #ifndef PK_R2_ROT
 #define PK_R2_ROT 1
 #endif
+#ifndef PK_DESC2L
+#define PK_DESC2L 1
+#endif
 #ifndef PK_DESC2
 #define PK_DESC2 1      // unlabelled pk_rect2 kernels: a rectangle's descriptor carries the addresses of its columns' data
 #endif
@@ -752,6 +755,7 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
     __shared__ long long s_work[2];
     __shared__ int s_pair[2];
     __shared__ __align__(8) int s_state[4];      // pk_rect2: parity, first level of the batch, slab base
+    __shared__ __align__(8) int s_cdist[2];      // labelled pk_rect2: distance of the b0 / b1 arrays, of the code arrays
     __shared__ int s_cntB[PK_MAX_CLASSES];
     __shared__ double s_part[32];
     __shared__ __align__(16) LevelDesc s_desc[PK_DESC_MAX];
@@ -771,6 +775,10 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
     // wavefront): in the tiers with two rows in flight, except the 56-register fp64 tier of 576 threads (1500 tips: 490 against
     // 497 Gcells/s with it)
     constexpr bool D2 = PK_DESC2 != 0 && RECT2 && !DEAL && (PK_DESC2 == 2 || (U == 2 && !(sizeof(T) == 8 && BOUND == 576)));
+    // labelled trees (chunk dealing): the same set-up, the two array distances in shared words of their own (the descriptor
+    // needs its words for the chunk numbering)
+    constexpr bool D2L = PK_DESC2L != 0 && RECT2 && DEAL && U == 2;
+    constexpr bool CONVC = D2 || D2L;      // the column's words are converted when the pair is staged
     constexpr bool PQ = RECT2 || (PK_PACKQ != 0 && STG != 0 &&
                         (PK_PACKQ == 2 || (sizeof(T) == 8 && !DEAL && (BOUND == 192 || BOUND == 320 || BOUND == 384))));
     unsigned char *const gstage = STG == 1 ? nullptr : a.stage + (size_t)blockIdx.x * (size_t)a.stage_stride;
@@ -966,7 +974,7 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
             for (int c = tid; c < nB; c += NT) {
                 b0w[c] *= (T)a.bscale;
                 b1w[c] *= (T)a.bscale;
-                if constexpr (D2) {      // the column's words as pk_rect2 uses them: rank - tag per child, parent code << 24
+                if constexpr (CONVC) {   // the column's words as pk_rect2 uses them: rank - tag per child, parent code << 24
                     int *c0w = const_cast<int *>(codeB0), *c1w = const_cast<int *>(codeB1), *pw = const_cast<int *>(pcB);
                     const int x0 = c0w[c], x1 = c1w[c];
                     c0w[c] = (x0 & 0xffffff) - (int)((unsigned)x0 & 0xff000000u);
@@ -989,6 +997,10 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
                 s_pair[0] = ia;
                 s_pair[1] = ib;
                 s_state[1] = 0;
+                if constexpr (D2L) {
+                    s_cdist[0] = lds_i32(sB32 + 28) - lds_i32(sB32 + 24);
+                    s_cdist[1] = lds_i32(sB32 + 36) - lds_i32(sB32 + 32);
+                }
             }
             // one column of one rectangle (descriptor at shared-memory address DP): fields r0, rows, wB, colbase, chunk_end, flags, nchunks, address of the first record
 #define PK_COLUMN2(DP, ROWS, JB)                                                                                                    \
@@ -1029,15 +1041,19 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
 #define PK_COLUMN2D(DP, Q1, JB)                                                                                                      \
     {                                                                                                                               \
         const int4 q2 = lds_i32x4((DP) + 16);                       /* {b1 - b0 distance, flags, code distance, first record} */    \
+        PK_COLUMN2X(Q1, q2.x, q2.z, q2.y, q2.w, JB)                                                                                 \
+    }
+#define PK_COLUMN2X(Q1, DIST_B, DIST_C, FLAGS, RA, JB)                                                                              \
+    {                                                                                                                               \
         const uint32_t ab = (uint32_t)(Q1).x + (uint32_t)sizeof(T) * (uint32_t)(JB), ac = (uint32_t)(Q1).w + 4u * (uint32_t)(JB);   \
         const T b0 = lds_real<T>(ab);                                                                                               \
-        const T b1 = lds_real<T>(ab + (uint32_t)q2.x);                                                                              \
-        const int cb0 = lds_i32(ac), cb1 = lds_i32(ac + (uint32_t)q2.z);                                                            \
-        const int pc = lds_i32(ac + 2u * (uint32_t)q2.z);                                                                           \
-        const uint32_t ra = (uint32_t)q2.w;                                                                                         \
+        const T b1 = lds_real<T>(ab + (uint32_t)(DIST_B));                                                                          \
+        const int cb0 = lds_i32(ac), cb1 = lds_i32(ac + (uint32_t)(DIST_C));                                                        \
+        const int pc = lds_i32(ac + 2u * (uint32_t)(DIST_C));                                                                       \
+        const uint32_t ra = (uint32_t)(RA);                                                                                         \
         unsigned long long base;                                                                                                    \
         asm volatile("ld.shared.u64 %0, [%1];" : "=l"(base) : "r"(smem_u32(&s_state[2])));                                          \
-        switch (q2.y & (512 | 1024)) {                                                                                              \
+        switch ((FLAGS) & (512 | 1024)) {                                                                                           \
         case 512 | 1024:                                                                                                            \
             acc = pk_rect2<T, false, false, U, DEAL, true>(ra, (Q1).y, (JB), b0, b1, cb0, cb1, pc, base, gk, sigma, tipf, acc);            \
             break;                                                                                                                  \
@@ -1075,11 +1091,11 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
                                 const int wB = s_cntB[c];
                                 d.r0 = r0; d.wB = wB; d.colbase = lds_i32(cls32 + 4 * c);
                                 d.pad1 = (int)(rec32 + 32u * (uint32_t)r0);          // shared-memory address of the first record
-                                if constexpr (D2) {      // (the code0, code1 and parent-code arrays are equally long)
+                                if constexpr (D2 || D2L) {      // (the code0, code1 and parent-code arrays are equally long)
                                     const int colbase = d.colbase;
                                     d.r0 = (int)(sB32 + (uint32_t)lds_i32(sB32 + 24) + (uint32_t)sizeof(T) * (uint32_t)colbase);
                                     d.colbase = (int)(sB32 + (uint32_t)lds_i32(sB32 + 32) + 4u * (uint32_t)colbase);
-                                    chunks = 0;
+                                    if constexpr (D2) chunks = 0;
                                 }
                                 if (rows > 0 && wB > 0) {
                                     d.rows = rows;
@@ -1140,6 +1156,13 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
                         for (int ch = tid >> 5; ch < nchunks; ch += NT >> 5) {
                             uint32_t dp = dl;
                             while (ch >= lds_i32(dp + 16)) dp += (uint32_t)sizeof(LevelDesc);      // uniform per warp, at most ncls steps
+                            if constexpr (D2L) {
+                                const int4 q1 = lds_i32x4(dp), q2 = lds_i32x4(dp + 16);      // {b0 address, rows, wB, code0 address}, {chunk end, flags, -, first record}
+                                const int2 dist = lds_i32x2(smem_u32(s_cdist));
+                                const int jb = ((ch - (q2.x - ((q1.z + 31) >> 5))) << 5) + (tid & 31);
+                                if (jb < q1.z) PK_COLUMN2X(q1, dist.x, dist.y, q2.y, q2.w, jb)
+                                continue;
+                            }
                             const int wB = lds_i32(dp + 8);
                             const int jb = ((ch - (lds_i32(dp + 16) - ((wB + 31) >> 5))) << 5) + (tid & 31);
                             if (jb < wB) PK_COLUMN2(dp, lds_i32(dp + 4), jb)
@@ -1173,6 +1196,7 @@ __global__ void __launch_bounds__(BOUND, (STG == 2     ? 2
             }
 #undef PK_COLUMN2
 #undef PK_COLUMN2D
+#undef PK_COLUMN2X
         } else {
         const int lev_per_batch = max(1, PK_DESC_MAX / ncls);
         for (int L0 = 0; L0 < nlevA; L0 += lev_per_batch) {
