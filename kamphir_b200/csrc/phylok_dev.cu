@@ -210,7 +210,10 @@ struct __align__(16) RowRec<double> {
     int off0, off1, st_off, packed;
 };
 
-// one (level, class) rectangle of the wavefront, precomputed per pair so the warps only read it
+// one (level, class) rectangle of the wavefront, precomputed per pair so the warps only read it.  In the PK_DESC2 kernels
+// (see the wavefront) r0 and colbase hold the shared-memory addresses of the rectangle's first column in the b0 and code0
+// arrays; for unlabelled trees chunk_end / nchunks hold the distances to the b1 and to the code1 / parent-code arrays and
+// bits 12-13 of the flags the slots to the next live descriptor.
 struct __align__(16) LevelDesc {
     int r0;         // first row (kernel order) of the rectangle
     int rows;       // rows at this level in this class (0: empty, skipped)
