@@ -20,7 +20,9 @@
 // octaves (fp64: table + degree-4 polynomial + integer exponent add, 8 fp64 instructions; fp32: one MUFU.EX2).
 // Stored cells live in shared memory for tiny pairs, otherwise in a per-CTA slab in HBM that stays L1/L2-resident:
 // coalesced group writes, software-pipelined child-cell gathers (fp32 and labelled trees: the pipeline also runs past the
-// end of a rectangle, PK_OVERRUN).  The kernel is instantiated per CTA-size tier (64 ... 1024 threads), each with the
+// end of a rectangle, PK_OVERRUN).  A pair is many short rectangles (~27 with gathers per 500-tip pair), so the code between
+// the row loops counts: per-level descriptors carry the addresses a thread needs to set up its column (PK_DESC2).
+// The kernel is instantiated per CTA-size tier (64 ... 1024 threads), each with the
 // register budget, resident CTAs per SM and rows in flight that measured best (table in DESIGN.md section 4).
 // No tensor cores (not a contraction), no CPU fallback.
 #include <cuda_runtime.h>
